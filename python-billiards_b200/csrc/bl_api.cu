@@ -1,0 +1,214 @@
+// bl_api.cu -- the extern "C" surface of libbilliards_b200.so (include/billiards_b200.h).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "bl_internal.h"
+
+int bl_set_error(bl_handle *h, int code, const char *fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return BL_OK;
+    return bl_set_error(h, BL_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+extern "C" {
+
+const char *bl_version(void) { return "billiards_b200 0.1 (sm_100a)"; }
+
+int bl_create(bl_handle **out, int device, int dot_fma) {
+    if (!out) return BL_EINVAL;
+    *out = nullptr;
+    bl_handle *h = new bl_handle();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->dot_fma = dot_fma ? 1 : 0;
+    *out = h;  // returned even on failure so that the caller can read the error text, then bl_destroy
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return bl_set_error(h, BL_EUNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                            prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = prop.sharedMemPerBlockOptin;
+    h->max_cluster = 16;
+    if ((e = cudaMalloc(&h->d_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
+    if ((e = cudaMallocHost(&h->h_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMallocHost");
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
+    return BL_OK;
+}
+
+int bl_destroy(bl_handle *h) {
+    if (!h) return BL_OK;
+    if (h->d_result) cudaFree(h->d_result);
+    if (h->h_result) cudaFreeHost(h->h_result);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return BL_OK;
+}
+
+const char *bl_last_error(const bl_handle *h) { return h ? h->err : "null handle"; }
+
+static int check_system(bl_handle *h, const bl_system *s) {
+    if (!h || !s) return BL_EINVAL;
+    if (s->n < 0 || s->pitch < s->n || (s->n > 0 && s->n_classes < 1))
+        return bl_set_error(h, BL_EINVAL, "bad system: n=%d pitch=%d classes=%d", s->n, s->pitch, s->n_classes);
+    return BL_OK;
+}
+
+int bl_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_recompute(h, s, time, d_idx, k, as_stream(stream));
+}
+
+int bl_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
+                   void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_apply_edits(h, s, time, d_pos, d_vel, as_stream(stream));
+}
+
+// libm pow through a volatile pointer so that no compiler folds pow(x, 2.0) into x*x
+static double (*volatile bl_libm_pow)(double, double) = pow;
+
+int bl_host_pow2_table(const double *r, int K, double *out, const double *R, int nd, double *out_disk) {
+    if (K < 0 || nd < 0 || (K > 0 && (!r || !out))) return BL_EINVAL;
+    for (int a = 0; a < K; a++)
+        for (int b = 0; b < K; b++) out[(size_t)a * K + b] = bl_libm_pow(r[a] + r[b], 2.0);
+    if (out_disk && R)
+        for (int q = 0; q < nd; q++)
+            for (int a = 0; a < K; a++) out_disk[(size_t)q * K + a] = bl_libm_pow(R[q] + r[a], 2.0);
+    return BL_OK;
+}
+
+int bl_rebuild_cover(bl_handle *h, const bl_system *s, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_rebuild_cover(h, s, as_stream(stream));
+}
+
+int bl_row_minima(bl_handle *h, const bl_system *s, double *d_balls_toi, int64_t *d_balls_idx, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_row_minima(h, s, d_balls_toi, d_balls_idx, as_stream(stream));
+}
+
+static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
+                      int first_kind, const bl_log *log, int query_only, bl_result *out, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    if (!out) return BL_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    if (s->n == 0) {  // an empty table only has a clock (tests/test_simulation.py:16-27 of the reference)
+        memset(out, 0, sizeof(*out));
+        out->time = query_only ? time : end_time;
+        out->bb_t = out->bo_t = __builtin_inf();
+        out->bb_i = -1; out->bb_j = 0; out->bo_ball = -1; out->bo_obs = -1;
+        return BL_OK;
+    }
+    cudaEventRecord(h->ev0, st);
+    rc = bl_launch_evolve(h, s, time, end_time, max_events, first_kind, log, query_only, st);
+    if (rc) return rc;
+    cudaEventRecord(h->ev1, st);
+    cudaError_t e = cudaMemcpyAsync(h->h_result, h->d_result, sizeof(bl_result), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "copy result");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "bl_evolve kernel");
+    cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+    *out = *h->h_result;
+    if (out->status != BL_OK)
+        return bl_set_error(h, out->status, "event kernel stopped with status %d at t=%.17g (balls %lld, %lld)",
+                            out->status, out->time, (long long)out->err_i, (long long)out->err_j);
+    return BL_OK;
+}
+
+int bl_evolve(bl_handle *h, const bl_system *s, double time, double end_time, int64_t max_events, int first_kind,
+              const bl_log *log, bl_result *out, void *stream) {
+    return run_evolve(h, s, time, end_time, max_events, first_kind, log, 0, out, stream);
+}
+
+int bl_next(bl_handle *h, const bl_system *s, double time, bl_result *out, void *stream) {
+    return run_evolve(h, s, time, time, 0, BL_ANY, nullptr, 1, out, stream);
+}
+
+int bl_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_positions(h, s, time, d_pos, as_stream(stream));
+}
+
+int bl_toi_ball_ball(bl_handle *h, const double *d_in, const double *d_rsum2, double t_eps, double *d_out, int64_t m,
+                     void *stream) {
+    if (!h) return BL_EINVAL;
+    return bl_launch_toi_batch(h, d_in, d_rsum2, t_eps, d_out, m, as_stream(stream));
+}
+
+int bl_elastic_collision(bl_handle *h, const double *d_in, double *d_out, int32_t *d_status, int64_t m, void *stream) {
+    if (!h) return BL_EINVAL;
+    return bl_launch_elastic_batch(h, d_in, d_out, d_status, m, as_stream(stream));
+}
+
+int bl_obstacle_detect(bl_handle *h, const bl_obstacle *obstacle, const double *d_in, const double *d_rsum2,
+                       double *d_out_t, double *d_out_arg, int64_t m, void *stream) {
+    if (!h || !obstacle) return BL_EINVAL;
+    return bl_launch_obstacle_detect(h, *obstacle, d_in, d_rsum2, d_out_t, d_out_arg, m, as_stream(stream));
+}
+
+int bl_obstacle_resolve(bl_handle *h, const bl_obstacle *obstacle, const double *d_in, const double *d_arg,
+                        double *d_out, int32_t *d_status, int64_t m, void *stream) {
+    if (!h || !obstacle) return BL_EINVAL;
+    return bl_launch_obstacle_resolve(h, *obstacle, d_in, d_arg, d_out, d_status, m, as_stream(stream));
+}
+
+int bl_ensemble_run(bl_handle *h, const bl_obstacle *obstacles_host, int n_obstacles, const double *rsum2_obs_host,
+                    double radius, int64_t n_sys, double *d_state, double *d_time, int64_t n_collisions,
+                    double end_time, int64_t *d_counts, int32_t *d_hits, int32_t *d_status, void *stream) {
+    if (!h || (n_obstacles > 0 && !obstacles_host)) return BL_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    cudaEventRecord(h->ev0, st);
+    int rc = bl_launch_ensemble(h, obstacles_host, n_obstacles, rsum2_obs_host, radius, n_sys, d_state, d_time,
+                                n_collisions, end_time, d_counts, d_hits, d_status, st);
+    cudaEventRecord(h->ev1, st);
+    return rc;
+}
+
+int bl_ensemble_stats(bl_handle *h, const int64_t *d_counts, const int32_t *d_hits, int n_obstacles, int64_t n_sys,
+                      int64_t *d_out, void *stream) {
+    if (!h) return BL_EINVAL;
+    return bl_launch_ensemble_stats(h, d_counts, d_hits, n_obstacles, n_sys, d_out, as_stream(stream));
+}
+
+int bl_last_kernel_ms(const bl_handle *h, float *ms) {
+    if (!h || !ms) return BL_EINVAL;
+    bl_handle *hh = const_cast<bl_handle *>(h);
+    if (cudaEventQuery(hh->ev1) == cudaSuccess) cudaEventElapsedTime(&hh->last_ms, hh->ev0, hh->ev1);
+    *ms = hh->last_ms;
+    return BL_OK;
+}
+
+int64_t bl_launch_count(const bl_handle *h) { return h ? h->launches : 0; }
+
+int bl_evolve_config(const bl_handle *h, int n, int *cluster, int *threads) {
+    if (!h || !cluster || !threads) return BL_EINVAL;
+    int bpt;
+    return bl_evolve_pick_config(h, n, cluster, threads, &bpt);
+}
+
+}  // extern "C"

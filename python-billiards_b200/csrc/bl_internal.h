@@ -1,0 +1,52 @@
+// bl_internal.h -- launcher prototypes shared by the translation units of libbilliards_b200.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/billiards_b200.h"
+
+struct bl_handle {
+    int device;
+    int dot_fma;
+    int sm_count;
+    int max_cluster;          // largest cluster size the event kernel may use on this device
+    size_t max_smem_optin;
+    bl_result *d_result;      // device result block
+    bl_result *h_result;      // pinned host mirror
+    cudaEvent_t ev0, ev1;
+    float last_ms;
+    long long launches;
+    char err[512];
+};
+
+#define BL_MAX_THREADS 1024
+#define BL_EVOLVE_BYTES_PER_BALL 160  // shared memory per resident ball in the event kernel (see bl_evolve.cu)
+
+int bl_set_error(bl_handle *h, int code, const char *fmt, ...);
+int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what);
+
+// bl_evolve.cu
+int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
+                     int first_kind, const bl_log *log, int query_only, cudaStream_t st);
+int bl_evolve_pick_config(const bl_handle *h, int n, int *cluster, int *threads, int *bpt);
+// bl_table.cu
+int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st);
+int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st);
+int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_t *d_idx, cudaStream_t st);
+int bl_launch_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
+                          cudaStream_t st);
+int bl_launch_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, cudaStream_t st);
+// bl_batch.cu
+int bl_launch_toi_batch(bl_handle *h, const double *d_in, const double *d_rsum2, double t_eps, double *d_out,
+                        long long m, cudaStream_t st);
+int bl_launch_elastic_batch(bl_handle *h, const double *d_in, double *d_out, int32_t *d_status, long long m,
+                            cudaStream_t st);
+int bl_launch_obstacle_detect(bl_handle *h, bl_obstacle ob, const double *d_in, const double *d_rsum2, double *d_t,
+                              double *d_arg, long long m, cudaStream_t st);
+int bl_launch_obstacle_resolve(bl_handle *h, bl_obstacle ob, const double *d_in, const double *d_arg, double *d_out,
+                               int32_t *d_status, long long m, cudaStream_t st);
+// bl_ensemble.cu
+int bl_launch_ensemble(bl_handle *h, const bl_obstacle *obs, int n_obs, const double *rsum2_obs, double radius,
+                       long long n_sys, double *d_state, double *d_time, long long n_coll, double end_time,
+                       int64_t *d_counts, int32_t *d_hits, int32_t *d_status, cudaStream_t st);
+int bl_launch_ensemble_stats(bl_handle *h, const int64_t *d_counts, const int32_t *d_hits, int n_obs, long long n_sys,
+                             int64_t *d_out, cudaStream_t st);

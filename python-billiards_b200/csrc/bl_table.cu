@@ -1,0 +1,152 @@
+// bl_table.cu -- time-of-impact table maintenance outside the event loop.
+//
+//   bl_recompute_kernel      add_ball's new row (simulation.py:176-209) and recompute_toi (:266-281): for each listed
+//                            ball, every pair with it is re-solved at the current time and stored in both triangles of
+//                            the symmetric table; its next-obstacle entry is refreshed.
+//   bl_rebuild_cover_kernel  per-ball candidate minima for the event kernel (full-row minimum, one warp per row).
+//   bl_row_minima_kernel     the reference-shaped _balls_toi/_balls_idx (:85-86, :184-191): minimum of the lower
+//                            triangle row, first index on ties, column 0 for an all-inf row, (inf,-1) for row 0.
+//   bl_positions_kernel      _move (:556-560) as a read-only projection: pos = p0 + v*(time - t0).
+#include "bl_arith.cuh"
+#include "bl_internal.h"
+
+namespace {
+
+template <bool FMA>
+__global__ void __launch_bounds__(256) bl_recompute_kernel(const bl_system S, const double time,
+                                                            const int32_t *__restrict__ idx) {
+    const int i = idx[blockIdx.y];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S.n) return;
+    const size_t pitch = (size_t)S.pitch;
+    const double ivx = S.vx[i], ivy = S.vy[i], it0 = S.t0[i];
+    const double ipx = bl_advance(S.p0x[i], ivx, time, it0), ipy = bl_advance(S.p0y[i], ivy, time, it0);
+    const int irc = S.rclass[i];
+    if (j == i) {
+        S.toi[(size_t)i * pitch + i] = BL_INF;
+        double ot, oarg;
+        int oi;
+        bl_next_obstacle<FMA>(S.obstacles, S.n_obstacles, S.rsum2_obs, S.n_classes, irc, ipx, ipy, ivx, ivy,
+                              S.radius[i], time, ot, oi, oarg);
+        S.obs_t[i] = ot; S.obs_idx[i] = oi; S.obs_arg[i] = oarg;
+        return;
+    }
+    const double jvx = S.vx[j], jvy = S.vy[j], jt0 = S.t0[j];
+    const double jpx = bl_advance(S.p0x[j], jvx, time, jt0), jpy = bl_advance(S.p0y[j], jvy, time, jt0);
+    const double rs = S.rsum2[(size_t)irc * S.n_classes + S.rclass[j]];
+    // _detect_ball_collision: time + toi_ball_ball (bit-symmetric in the two balls)
+    const double v = bl_add(time, bl_toi_ball_ball<FMA>(ipx, ipy, ivx, ivy, jpx, jpy, jvx, jvy, rs));
+    S.toi[(size_t)i * pitch + j] = v;
+    S.toi[(size_t)j * pitch + i] = v;
+}
+
+__device__ __forceinline__ void warp_min_key(uint64_t &ts, uint64_t &cd) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t t2 = __shfl_xor_sync(0xffffffffu, ts, o), c2 = __shfl_xor_sync(0xffffffffu, cd, o);
+        if (bl_key_less(t2, c2, ts, cd)) { ts = t2; cd = c2; }
+    }
+}
+
+__global__ void __launch_bounds__(256) bl_rebuild_cover_kernel(const bl_system S) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= S.n) return;
+    const double *row = S.toi + (size_t)k * S.pitch;
+    uint64_t ts = ~0ull, cd = BL_CODE_END;
+    for (int x = lane; x < S.n; x += 32) {
+        const double v = row[x];
+        if (x != k && v < BL_INF) {
+            const uint64_t s2 = bl_sortable(v), c2 = bl_pair_code(k, x);
+            if (bl_key_less(s2, c2, ts, cd)) { ts = s2; cd = c2; }
+        }
+    }
+    warp_min_key(ts, cd);
+    if (lane == 0) {
+        if (cd == BL_CODE_END) { S.cover_t[k] = BL_INF; S.cover_code[k] = BL_CODE_NONE; }
+        else { S.cover_t[k] = bl_unsortable(ts); S.cover_code[k] = cd; }
+    }
+}
+
+__global__ void __launch_bounds__(256) bl_row_minima_kernel(const bl_system S, double *__restrict__ out_t,
+                                                             int64_t *__restrict__ out_idx) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= S.n) return;
+    if (i == 0) {
+        if (lane == 0) { out_t[0] = BL_INF; out_idx[0] = -1; }
+        return;
+    }
+    const double *row = S.toi + (size_t)i * S.pitch;
+    uint64_t ts = ~0ull, cd = BL_CODE_END;
+    for (int x = lane; x < i; x += 32) {
+        const uint64_t s2 = bl_sortable(row[x]), c2 = (uint64_t)x;
+        if (bl_key_less(s2, c2, ts, cd)) { ts = s2; cd = c2; }
+    }
+    warp_min_key(ts, cd);
+    if (lane == 0) { out_t[i] = bl_unsortable(ts); out_idx[i] = (int64_t)cd; }
+}
+
+__global__ void __launch_bounds__(256) bl_positions_kernel(const bl_system S, const double time,
+                                                            double *__restrict__ pos) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.n) return;
+    const double t0 = S.t0[k];
+    pos[2 * k] = bl_advance(S.p0x[k], S.vx[k], time, t0);
+    pos[2 * k + 1] = bl_advance(S.p0y[k], S.vy[k], time, t0);
+}
+
+// recompute_toi's edit detection, simulation.py:255-260
+__global__ void __launch_bounds__(256) bl_apply_edits_kernel(const bl_system S, const double time,
+                                                              const double *__restrict__ pos,
+                                                              const double *__restrict__ vel) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.n) return;
+    const double vx = vel[2 * k], vy = vel[2 * k + 1], t0 = S.t0[k];
+    const double ox = bl_advance(S.p0x[k], vx, time, t0), oy = bl_advance(S.p0y[k], vy, time, t0);
+    const double px = pos[2 * k], py = pos[2 * k + 1];
+    S.vx[k] = vx; S.vy[k] = vy;
+    if (px != ox || py != oy) { S.t0[k] = time; S.p0x[k] = px; S.p0y[k] = py; }
+}
+
+}  // namespace
+
+int bl_launch_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
+                          cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    bl_apply_edits_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(*s, time, d_pos, d_vel);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_apply_edits_kernel");
+}
+
+int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st) {
+    if (k <= 0 || s->n <= 0) return BL_OK;
+    const int chunk = 32768;  // gridDim.y limit is 65535
+    for (int off = 0; off < k; off += chunk) {
+        const int kk = k - off < chunk ? k - off : chunk;
+        dim3 grid((unsigned)((s->n + 255) / 256), (unsigned)kk, 1);
+        if (h->dot_fma) bl_recompute_kernel<true><<<grid, 256, 0, st>>>(*s, time, d_idx + off);
+        else bl_recompute_kernel<false><<<grid, 256, 0, st>>>(*s, time, d_idx + off);
+        h->launches++;
+    }
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_recompute_kernel");
+}
+
+int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    bl_rebuild_cover_kernel<<<(unsigned)((s->n + 7) / 8), 256, 0, st>>>(*s);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_rebuild_cover_kernel");
+}
+
+int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_t *d_idx, cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    bl_row_minima_kernel<<<(unsigned)((s->n + 7) / 8), 256, 0, st>>>(*s, d_toi, d_idx);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_row_minima_kernel");
+}
+
+int bl_launch_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    bl_positions_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(*s, time, d_pos);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_positions_kernel");
+}

@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C ABI, via the drop-in Python API) with the golden vectors of the live
+reference and with the CPU oracle on the same seeded inputs.  Bit-exact for event order, times and state."""
+
+import numpy as np
+import pytest
+
+import workloads
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+INF = float("inf")
+
+
+@pytest.fixture(scope="module")
+def billiards():
+    import billiards as pkg
+    return pkg
+
+
+def build(billiards, cfg, fma, one_by_one=False):
+    bld = billiards.Billiard(workloads.make_obstacles(billiards, cfg.obstacles), dot_fma=fma)
+    if one_by_one:
+        for k in range(cfg.n):
+            bld.add_ball(tuple(cfg.pos[k]), tuple(cfg.vel[k]), float(cfg.radius[k]), float(cfg.mass[k]))
+    else:
+        bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
+    return bld
+
+
+LOGGED = [
+    ("pool", workloads.pool, dict(end_time=100.0)),
+    ("hetero_gas", workloads.hetero_gas, dict(n_events=4000)),
+    ("dense_gas_256", lambda: workloads.dense_gas(16), dict(n_events=2000)),
+    ("dense_gas_1024", lambda: workloads.dense_gas(32), dict(n_events=1000)),
+    ("ideal_gas_1024", lambda: workloads.ideal_gas(32), dict(n_events=1000)),
+]
+
+
+@pytest.mark.parametrize("name,make,kw", LOGGED, ids=[c[0] for c in LOGGED])
+def test_event_log_matches_reference(billiards, golden, name, make, kw):
+    g = golden(name)
+    fma = bool(g["dot_fma"])
+    bld = build(billiards, make(), fma)
+    # table state right after the build
+    assert_bits_equal(bld._balls_toi, g["start_balls_toi"], "initial _balls_toi")
+    assert [int(x) for x in bld._balls_idx] == g["start_balls_idx"].tolist()
+    assert_bits_equal(bld._obstacles_toi, g["start_obs_toi"], "initial _obstacles_toi")
+    if "start_toi_tri" in g:
+        assert_bits_equal(np.concatenate(bld.toi_table), g["start_toi_tri"], "initial toi_table")
+    if "end_time" in kw:
+        counts, (t, i, j) = bld.evolve_events(10**9, end_time=kw["end_time"], log_capacity=len(g["log_t"]) + 8)
+    else:
+        counts, (t, i, j) = bld.evolve_events(kw["n_events"], log_capacity=kw["n_events"])
+    assert len(t) == len(g["log_t"])
+    assert i.tolist() == g["log_i"].tolist()
+    assert j.tolist() == g["log_j"].tolist()
+    assert_bits_equal(t, g["log_t"], "event times")
+    assert counts == (int((g["log_j"] >= 0).sum()), int((g["log_j"] < 0).sum()))
+    if "end_time" in kw:
+        assert bld.time == float(g["end_time"])
+        assert_bits_equal(bld.balls_position, g["end_pos"], "end positions")
+    assert_bits_equal(bld.balls_velocity, g["end_vel"], "end velocities")
+    assert_bits_equal(bld.balls_initial_position, g["end_p0"], "end initial positions")
+    assert_bits_equal(bld.balls_initial_time[:, 0], g["end_t0"], "end initial times")
+    assert_bits_equal(bld._balls_toi, g["end_balls_toi"], "_balls_toi")
+    assert [int(x) for x in bld._balls_idx] == g["end_balls_idx"].tolist()
+    assert_bits_equal(bld._obstacles_toi, g["end_obs_toi"], "_obstacles_toi")
+    nb = bld.next_ball_ball_collision
+    assert_bits_equal([nb[0]], g["end_next_bb"][:1])
+    assert list(nb[1:]) == g["end_next_bb"][1:].astype(int).tolist()
+    no = bld.next_ball_obstacle_collision
+    assert_bits_equal([no[0]], g["end_next_bo"][:1])
+    assert no[1] == int(g["end_next_bo"][1])
+    if "end_toi_tri" in g:
+        assert_bits_equal(np.concatenate(bld.toi_table), g["end_toi_tri"], "toi_table")
+
+
+def test_pool_payload_and_one_by_one_build(billiards, golden):
+    g = golden("pool")
+    bld = build(billiards, workloads.pool(), bool(g["dot_fma"]), one_by_one=True)
+    counts, (t, i, j, p) = bld.evolve_events(10**9, end_time=100.0, log_capacity=512, payload=True)
+    assert counts == (167, 248)
+    assert_bits_equal(t, g["log_t"])
+    assert_bits_equal(p, g["log_payload"], "callback payloads")
+
+
+def test_galperin_exact(billiards, golden):
+    """314159 collisions for mass ratio 100**5 (README.md:134-135, docs/quickstart.rst:50-131 of the reference)."""
+    g = golden("galperin")
+    fma = bool(g["dot_fma"])
+    cfg = workloads.galperin()
+    bld = build(billiards, cfg, fma, one_by_one=True)
+    assert bld.next_collision == (1.8000000000000005, 0, 1)
+    total, cum = 0, []
+    for t in (1, 2, 3, 4, 5):
+        total += sum(bld.evolve(t))
+        cum.append(total)
+    assert cum == [0, 1, 1, 4, 314152]
+    total += sum(bld.evolve(16))
+    assert total == 314159
+    assert bld.balls_velocity[0, 0] == float.fromhex("0x1.78217eaf374a7p-1")
+    assert_bits_equal(bld.balls_position, g["end_pos"])
+    assert_bits_equal(bld.balls_velocity, g["end_vel"])
+    v, m = bld.balls_velocity, np.asarray(bld.balls_mass)
+    assert float((m * (v * v).sum(axis=1)).sum() / 2) == 4999999999.989935
+    assert bld.next_ball_ball_collision == (INF, -1, 0)
+    assert bld.next_ball_obstacle_collision == (INF, 0, None)
+    one = build(billiards, cfg, fma)
+    assert one.evolve(16) == (157080, 157079)
+    logged = build(billiards, cfg, fma)
+    _, (t, i, j) = logged.evolve_events(20000, log_capacity=20000)
+    assert_bits_equal(t, g["log_t"])
+    assert i.tolist() == g["log_i"].tolist() and j.tolist() == g["log_j"].tolist()
+
+
+@pytest.mark.parametrize("n_side,n_events", [(8, 3000), (23, 1500), (40, 600)])
+def test_against_oracle_seeded(billiards, oracle, n_side, n_events):
+    """Sizes and seeds the golden files do not cover (odd N -> partially filled warps, N > 1024 -> clusters)."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.dense_gas(n_side, seed=n_side, phi=0.35)
+    bld = build(billiards, cfg, fma)
+    ref = cfg.build_oracle(oracle, dot_fma=fma, flags=oracle.FAST_ROWMIN)
+    ref.enable_log(n_events)
+    ref.evolve(INF, max_events=n_events)
+    rt, ri, rj = ref.log()
+    _, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+    assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+    assert_bits_equal(t, rt, "event times")
+    st = ref.state()
+    assert_bits_equal(bld.balls_velocity, st["v"])
+    assert_bits_equal(bld.balls_initial_position, st["p0"])
+    bt, bi, ot, oo, _ = ref.minima()
+    assert_bits_equal(bld._balls_toi, bt)
+    assert [int(x) for x in bld._balls_idx] == bi.tolist()
+    assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
+
+
+def test_stop_resume_is_bit_stable(billiards, oracle):
+    """tests/test_simulation.py:461-502: 300 partial evolves == one evolve, exactly; and == the oracle."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.Config("four", workloads.box_walls(-1, -1, 1, 1), [(0, 0.2), (0, 0.5), (0, -0.8), (0.7, -0.8)],
+                           [(1, 2), (-1, 2), (0, -1), (0, 0)], 0.2, 1.0)
+    once, step = build(billiards, cfg, fma), build(billiards, cfg, fma)
+    once.evolve(10)
+    for i in range(10):
+        for j in range(1, 31):
+            step.evolve(i + j / 30)
+    assert np.linalg.norm(once.balls_position - step.balls_position, axis=1).max() == 0
+    ref = cfg.build_oracle(oracle, dot_fma=fma)
+    ref.evolve(10)
+    assert_bits_equal(once.balls_position, ref.balls_position)
+
+
+def test_recompute_scenario(billiards, golden):
+    g = golden("four_balls")
+    fma = bool(g["dot_fma"])
+    cfg = workloads.Config("four", workloads.box_walls(-1, -1, 1, 1), [(0, 0.2), (0, 0.5), (0, -0.8), (0.7, -0.8)],
+                           [(1, 2), (-1, 2), (0, -1), (0, 0)], 0.2, 1.0)
+
+    def check(b, tag):
+        assert_bits_equal(np.concatenate(b.toi_table), g[tag + "_toi_tri"], tag + " table")
+        assert_bits_equal(b._balls_toi, g[tag + "_balls_toi"], tag)
+        assert [int(x) for x in b._balls_idx] == g[tag + "_balls_idx"].tolist()
+        assert_bits_equal(b._obstacles_toi, g[tag + "_obs_toi"], tag)
+        assert_bits_equal(b.balls_position, g[tag + "_pos"], tag)
+        assert_bits_equal(b.balls_initial_time[:, 0], g[tag + "_t0"], tag)
+
+    b = build(billiards, cfg, fma, one_by_one=True)
+    b.evolve(1)
+    b.balls_position[0] = (0, 0)
+    b.recompute_toi(0)
+    assert b.time == 1
+    check(b, "s1")
+    b.evolve(2)
+    b.balls_velocity[1] = (0, 0)
+    b.balls_radius[2] = 0.1
+    b.recompute_toi([1, 2])
+    check(b, "s2")
+    b.evolve(3)
+    b.recompute_toi()
+    check(b, "s3")
+    assert b.evolve(5) == tuple(g["counts5"].tolist())
+    check(b, "s5")
+
+
+def test_cradle_nudge(billiards, golden):
+    g = golden("cradle")
+    b = build(billiards, workloads.newtons_cradle(5, True), bool(g["dot_fma"]), one_by_one=True)
+    assert b.next_ball_ball_collision == tuple(g["next_bb"].tolist())
+    _, (t, i, j) = b.evolve_events(10**6, end_time=4.0, log_capacity=64)
+    assert_bits_equal(t, g["log_t"])
+    assert (i.tolist(), j.tolist()) == (g["log_i"].tolist(), g["log_j"].tolist())
+    b.balls_position[2] += (0, 1e-10)
+    b.recompute_toi(2)
+    assert_bits_equal(np.concatenate(b.toi_table), g["nudge_toi_tri"])
+    assert b.evolve(30) == tuple(g["counts30"].tolist())
+    assert_bits_equal(b.balls_position, g["end_pos"])
+
+
+def test_sinai_ensemble(billiards, golden, oracle):
+    g = golden("sinai")
+    fma = bool(g["dot_fma"])
+    obstacles, pos, vel = workloads.sinai(64, seed=0)
+    ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, dot_fma=fma,
+                                     count_hits=True)
+    ens.run(int(g["n_coll"]))
+    assert_bits_equal(ens.time, g["t"])
+    assert_bits_equal(ens.balls_initial_position, g["p0"])
+    assert_bits_equal(ens.balls_velocity, g["v"])
+    assert ens.hits.tolist() == g["hits"].tolist()
+    assert ens.gather_stats().tolist() == [64 * int(g["n_coll"])] + g["hits"].sum(axis=0).tolist()
+    # resumability: 2 x 1000 == 1 x 2000, and a bigger seeded batch against the oracle loop
+    two = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, dot_fma=fma)
+    two.run(1000)
+    two.run(1000)
+    assert_bits_equal(two.time, g["t"])
+    obstacles, pos, vel = workloads.sinai(20000, seed=5)
+    big = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, dot_fma=fma)
+    big.run(300)
+    want = oracle.ensemble_run(workloads.oracle_obstacles(obstacles), pos, vel, 300, dot_fma=fma)
+    assert_bits_equal(big.time, want["t"])
+    assert_bits_equal(big.balls_velocity, want["v"])
+    assert_bits_equal(big.balls_initial_position, want["p0"])
+    # the same single system through Billiard
+    one = billiards.Billiard(workloads.make_obstacles(billiards, obstacles), dot_fma=fma)
+    one.add_ball(pos[7], vel[7], radius=0)
+    assert one.evolve_events(300) == (0, 300)
+    assert one.time == want["t"][7]
+
+
+def test_unit_vectors(billiards, golden):
+    from billiards import physics
+    g = golden("unit_vectors")
+    fma = bool(g["dot_fma"])
+    toi = physics.toi_ball_ball_batch(g["p1"], g["v1"], g["r1"], g["p2"], g["v2"], g["r2"], dot_fma=fma)
+    assert_bits_equal(toi, g["toi"], "toi_ball_ball")
+    w1, w2, st = physics.elastic_collision_batch(g["q1"], g["u1"], g["m1"], g["q2"], g["u2"], g["m2"], dot_fma=fma)
+    ok = g["sep"] == 0
+    assert ((st == 0) == ok).all() and (st[~ok] == -3).all()
+    assert_bits_equal(w1[ok], g["w1"][ok])
+    assert_bits_equal(w2[ok], g["w2"][ok])
+
+
+def test_pow_is_libm_not_square(billiards, oracle):
+    """(r1+r2)**2 goes through libm pow like CPython's float.__pow__: a radius sum for
+    which pow(s, 2) != s*s on glibc must give the oracle's (= the reference's) bits."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    s = 8.237813583927716
+    r1 = 3.0
+    r2 = s - r1
+    assert r1 + r2 == s
+    cfg = workloads.Config("pow", [], [(0.0, 0.0), (20.0, 0.3)], [(1.0, 0.0), (-1.0, 0.0)], [r1, r2], 1.0)
+    b = build(billiards, cfg, fma)
+    ref = cfg.build_oracle(oracle, dot_fma=fma)
+    assert_bits_equal(np.concatenate(b.toi_table), np.concatenate(ref.toi_table))
