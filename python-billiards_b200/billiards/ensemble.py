@@ -48,15 +48,19 @@ class BilliardEnsemble:
         # (R + r)**2 with Python floats, like Disk.detect_collision -> toi_ball_ball does (physics.py:52)
         self._rsum2 = np.asarray([float((o.radius + self.radius) ** 2) if r.kind == _lib.BL_OBS_DISK else 0.0
                                   for o, r in zip(self.obstacles, self._records)] or [0.0], dtype=np.float64)
-        pos = np.asarray(pos, dtype=np.float64).reshape(-1, 2)
-        vel = np.asarray(vel, dtype=np.float64).reshape(-1, 2)
-        if pos.shape != vel.shape:
-            raise ValueError(f"pos and vel must have the same shape, got {pos.shape} and {vel.shape}")
-        self.n = pos.shape[0]
+        # numpy arrays or (pinned) torch CPU tensors of shape (n, 2); the H2D copy is asynchronous for pinned input
+        pos_t = pos if isinstance(pos, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))
+        vel_t = vel if isinstance(vel, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vel, dtype=np.float64))
+        pos_t, vel_t = pos_t.reshape(-1, 2), vel_t.reshape(-1, 2)
+        if pos_t.shape != vel_t.shape or pos_t.dtype != torch.float64 or vel_t.dtype != torch.float64:
+            raise ValueError(f"pos and vel must be float64 arrays of the same shape, got {tuple(pos_t.shape)} and "
+                             f"{tuple(vel_t.shape)}")
+        self.n = pos_t.shape[0]
         self._handle = _lib.get_handle(device, dot_fma)
         dev = self._handle.torch_device
-        host = np.concatenate([pos.T, vel.T, np.zeros((1, self.n))], axis=0)  # SoA [5][n]: p0x p0y vx vy t0
-        self._state = torch.from_numpy(np.ascontiguousarray(host)).to(dev)
+        self._state = torch.zeros((5, self.n), dtype=torch.float64, device=dev)  # SoA: p0x p0y vx vy t0
+        self._state[0:2].copy_(pos_t.to(dev, non_blocking=True).T)
+        self._state[2:4].copy_(vel_t.to(dev, non_blocking=True).T)
         self._time = torch.zeros(self.n, dtype=torch.float64, device=dev)
         self._counts = torch.zeros(self.n, dtype=torch.int64, device=dev)
         self._status = torch.zeros(self.n, dtype=torch.int32, device=dev)

@@ -33,6 +33,7 @@ LOGGED = [
     ("dense_gas_256", lambda: workloads.dense_gas(16), dict(n_events=2000)),
     ("dense_gas_1024", lambda: workloads.dense_gas(32), dict(n_events=1000)),
     ("ideal_gas_1024", lambda: workloads.ideal_gas(32), dict(n_events=1000)),
+    ("dense_gas_16384", lambda: workloads.dense_gas(128), dict(n_events=100)),
 ]
 
 

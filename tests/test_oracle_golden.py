@@ -60,6 +60,20 @@ def test_event_log_bit_exact(oracle, golden, name, make, kw, flags):
         assert_bits_equal(np.concatenate(o.toi_table), g["end_toi_tri"], "toi_table")
 
 
+def test_headline_config_prefix(oracle, golden):
+    """N = 16384 dense gas (BASELINE.json config D): first 100 collisions of the live reference (recorded with
+    make_golden.py --big, 500 s of add_ball + 24 s of events there)."""
+    g = golden("dense_gas_16384")
+    o = workloads.dense_gas(128).build_oracle(oracle, dot_fma=bool(g["dot_fma"]), flags=oracle.FAST_ROWMIN)
+    t, i, j = run_logged(o, n_events=100)
+    assert_bits_equal(t, g["log_t"], "event times")
+    assert (i.tolist(), j.tolist()) == (g["log_i"].tolist(), g["log_j"].tolist())
+    assert_bits_equal(o.state()["v"], g["end_vel"])
+    bt, bi, ot, oo, _ = o.minima()
+    assert_bits_equal(bt, g["end_balls_toi"])
+    assert bi.tolist() == g["end_balls_idx"].tolist()
+
+
 def test_wrong_dot_mode_diverges(oracle, golden):
     """the un-fused dot does not reproduce the reference (times differ in the last bits,
     and in a chaotic gas the order follows) -- the dot mode is part of the contract."""
