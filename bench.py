@@ -153,6 +153,7 @@ def bench_gas(args, device, fma):
     n_bb = n_bo = 0
     kernel_ms = 0.0
     rescans = 0
+    prof = [0] * 8
     barrier(device)
     ev0.record()
     for _ in range(args.steps):
@@ -161,6 +162,7 @@ def bench_gas(args, device, fma):
         n_bo += c[1]
         kernel_ms += h.last_kernel_ms()
         rescans += int(bld.last_result.n_rescans)
+        prof = [a + int(b) for a, b in zip(prof, bld.last_result.prof)]
     ev1.record()
     barrier(device)
     clocks = sampler.stop()
@@ -220,6 +222,9 @@ def bench_gas(args, device, fma):
                    "l2": "inputs larger than L2 (table 2.1 GB, one event touches 4 rows/columns of it)",
                    "cluster": list(_evolve_config(h, N)), "dot_fma": bool(fma)},
         "counts": {"ball_ball": n_bb, "ball_obstacle": n_bo, "stale_row_rescans": rescans},
+        "phase_cycles_per_event": {k: prof[q] / max(n_bb + n_bo, 1) for q, k in
+                                   enumerate(("argmin_and_barrier", "resolve", "solve_and_update", "stale_row_repair"))},
+        "repair_phases": prof[4], "loop_iterations": prof[5],
         "build_seconds": build_s,
     }, cfg
 
@@ -420,6 +425,8 @@ def main():
         gas, _ = bench_gas(args, device, fma)
         line.update({k: gas[k] for k in ("value", "ms_per_step", "config", "roofline", "e2e", "clocks", "gpu_launches")})
         line["counts"] = gas["counts"]
+        line["phase_cycles_per_event"] = gas["phase_cycles_per_event"]
+        line["repair_phases"] = gas["repair_phases"]
         line["table_build_seconds"] = gas["build_seconds"]
         ens_steps = max(1, min(args.steps, 3))
         ens = bench_ensemble(args, device, fma, rank, world, ens_steps, 1)

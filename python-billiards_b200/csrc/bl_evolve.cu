@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
     long long bb_i = -1, bb_j = 0, bo_ball = -1, bo_obs = -1;
     if (final_stage == 1) mode = MODE_BB;
 
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (;;) {
+        const long long c0 = clock64();
+        prof[5]++;
         // ---- argmin, thread level: best candidate among the owned balls ----------------------------
         uint64_t best_ts = ~0ull, best_code = BL_CODE_END;
         int best_kl = 0;
@@ -261,6 +264,8 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
             }
         }
         cluster_sync_all();
+        const long long c1 = clock64();
+        prof[0] += c1 - c0;
         // ---- cluster level + resolve: warp 0 of every CTA redundantly --------------------------------
         if (warp == 0) {
             const uint64_t *box = &M.inbox[parity * 16 * NW_PAD];
@@ -360,6 +365,8 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
         }
         parity ^= 1;
         __syncthreads();
+        const long long c2 = clock64();
+        prof[1] += c2 - c1;
 
         const int kind = bc.kind;
         if (kind == EV_RESCAN) {
@@ -400,6 +407,8 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
             n_rescans += nd;  // per-CTA count; summed over CTAs at the end
             __syncthreads();
             if (tid == 0) *M.n_dirty = 0;
+            prof[3] += clock64() - c2;
+            prof[4]++;
             continue;
         }
         if (kind == EV_STOP) {
@@ -499,6 +508,7 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
         if (kind == EV_BB) n_bb++; else n_bo++;
         if (P.log.cap > 0) n_logged++;
         mode = MODE_BOTH;
+        prof[2] += clock64() - c2;
         // no barrier needed here: the next writer of `bc` is warp 0 after the next __syncthreads pair
     }
 
@@ -517,6 +527,7 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
         r->bb_t = bb_t; r->bb_i = bb_i; r->bb_j = bb_j;
         r->bo_t = bo_t; r->bo_ball = bo_ball; r->bo_obs = bo_obs; r->bo_arg = bo_arg;
         r->status = status; r->stop = stop; r->n_logged = n_logged; r->err_i = err_i; r->err_j = err_j;
+        for (int q = 0; q < 8; q++) r->prof[q] = prof[q];
     }
     cluster_sync_all();  // nobody exits while a peer may still post into its inbox
 }
