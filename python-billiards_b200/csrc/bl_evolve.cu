@@ -284,13 +284,14 @@ __global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Para
             } else if (final_stage) {
                 kind = EV_STOP;
             } else if (cd == BL_CODE_NONE || cd == BL_CODE_END) {
-                kind = EV_STOP; stop_local = BL_STOP_TIME;
+                kind = EV_STOP;
+                stop_local = (P.max_events >= 0 && events >= P.max_events) ? BL_STOP_EVENTS : BL_STOP_TIME;
             } else if (ts == BL_TS_NAN) {
                 kind = EV_STOP; st_local = BL_ENAN; stop_local = BL_STOP_ERROR;
+            } else if (P.max_events >= 0 && events >= P.max_events) {
+                kind = EV_STOP; stop_local = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
             } else if (!(t <= P.end_time) || t == BL_INF) {
                 kind = EV_STOP; stop_local = BL_STOP_TIME;
-            } else if (P.max_events >= 0 && events >= P.max_events) {
-                kind = EV_STOP; stop_local = BL_STOP_EVENTS;
             } else if (P.log.cap > 0 && n_logged >= P.log.cap) {
                 kind = EV_STOP; stop_local = BL_STOP_LOG;
             } else if (cd & BL_CODE_OBS) {
