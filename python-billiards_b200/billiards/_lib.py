@@ -44,7 +44,7 @@ class BlResult(ctypes.Structure):
                 ("bo_t", ctypes.c_double), ("bo_ball", ctypes.c_int64), ("bo_obs", ctypes.c_int64),
                 ("bo_arg", ctypes.c_double), ("status", ctypes.c_int32), ("stop", ctypes.c_int32),
                 ("n_logged", ctypes.c_int64), ("n_rescans", ctypes.c_int64), ("err_i", ctypes.c_int64),
-                ("err_j", ctypes.c_int64), ("prof", ctypes.c_int64 * 8)]
+                ("err_j", ctypes.c_int64), ("prof", ctypes.c_int64 * 8), ("window", ctypes.c_double)]
 
 
 class BlLog(ctypes.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "bl_last_kernel_ms": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_float)]),
     "bl_launch_count": (ctypes.c_int64, [_H]),
     "bl_evolve_config": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bl_set_batch_target": (ctypes.c_int, [_H, ctypes.c_int]),
 }
 
 _lib = None

@@ -48,6 +48,10 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
     h->max_cluster = 16;
     if ((e = cudaMalloc(&h->d_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMallocHost(&h->h_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMallocHost");
+    if ((e = cudaMalloc(&h->d_bar, 64)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
+    if ((e = cudaMalloc(&h->d_post, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_POST_WORDS)) != cudaSuccess)
+        return bl_check_cuda(h, e, "cudaMalloc");
+    if ((e = cudaMalloc(&h->d_viol, sizeof(uint64_t) * 2 * BL_MAX_CTAS)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     return BL_OK;
@@ -56,6 +60,9 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
 int bl_destroy(bl_handle *h) {
     if (!h) return BL_OK;
     if (h->d_result) cudaFree(h->d_result);
+    if (h->d_bar) cudaFree(h->d_bar);
+    if (h->d_post) cudaFree(h->d_post);
+    if (h->d_viol) cudaFree(h->d_viol);
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -133,6 +140,7 @@ static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_
     if (e != cudaSuccess) return bl_check_cuda(h, e, "bl_evolve kernel");
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     *out = *h->h_result;
+    if (!query_only) { h->window = out->window; h->window_n = s->n; h->window_sys = (const void *)s->toi; }
     if (out->status != BL_OK)
         return bl_set_error(h, out->status, "event kernel stopped with status %d at t=%.17g (balls %lld, %lld)",
                             out->status, out->time, (long long)out->err_i, (long long)out->err_j);
@@ -205,10 +213,16 @@ int bl_last_kernel_ms(const bl_handle *h, float *ms) {
 
 int64_t bl_launch_count(const bl_handle *h) { return h ? h->launches : 0; }
 
-int bl_evolve_config(const bl_handle *h, int n, int *cluster, int *threads) {
-    if (!h || !cluster || !threads) return BL_EINVAL;
-    int bpt;
-    return bl_evolve_pick_config(h, n, cluster, threads, &bpt);
+int bl_evolve_config(const bl_handle *h, int n, int *ctas, int *threads) {
+    if (!h || !ctas || !threads) return BL_EINVAL;
+    int sync_mode;
+    return bl_evolve_pick_config(h, n, ctas, threads, &sync_mode);
+}
+
+int bl_set_batch_target(bl_handle *h, int target) {
+    if (!h || target < 0) return BL_EINVAL;
+    h->target_override = target;
+    return BL_OK;
 }
 
 }  // extern "C"

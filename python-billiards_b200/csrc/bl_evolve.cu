@@ -1,28 +1,45 @@
-// bl_evolve.cu -- the event loop of Billiard.evolve as ONE persistent kernel.
+// bl_evolve.cu -- the event loop of Billiard.evolve as ONE persistent, grid-wide kernel that commits BATCHES of
+// causally independent collisions per synchronisation round, in exactly the reference's order and with exactly
+// the reference's bits.
 //
 // Replaces simulation.py:354-438 (evolve), :440-502 (bounce_ball_ball), :504-554 (bounce_ball_obstacle),
 // :556-560 (_move), :562-636 (_resolve_*), with physics.py:10-76/:255-282 and obstacles.py:70-76/:112-144
 // inlined from bl_arith.cuh.
 //
-// Shape of the computation: events are strictly serial (each needs a global argmin and changes state the
-// next one reads), so the kernel is latency-bound; it runs as ONE thread-block cluster (1..16 CTAs on
-// neighbouring SMs) whose barrier costs a few hundred cycles instead of a grid-wide sync:
-//   - every ball is owned by one thread; its state of record (p0, v, t0, mass, radius), its candidate minimum
-//     and its next-obstacle entry stay resident in that CTA's shared memory for the whole launch;
-//   - the all-pairs table of absolute impact times stays in HBM/L2 (symmetric, n x pitch doubles); per event the
-//     owners of all other balls solve their pair with the colliding ball(s) (2(N-2) solves) and store the row
-//     entry (coalesced) and the column entry (strided);
-//   - the argmin is a warp REDUX -> CTA -> cluster reduction over (time, code) keys whose lexicographic order
-//     reproduces numpy's first-index tie-breaking; CTA winners are exchanged through distributed shared memory.
+// Why batches.  The reference handles one collision per iteration: global argmin -> resolve -> 2(N-2) pair
+// solves -> argmin ...  One iteration is a chain of dependent steps (reduction, broadcast, solve), so a kernel
+// that follows it literally is bound by synchronisation latency, microseconds per event whatever the bandwidth.
+// But in a system of N balls the next few dozen collisions almost always involve different balls and do not
+// influence each other: collision e2 is "the next one after e1" as long as nothing e1 produces (the new impact
+// times of its two balls) comes earlier than e2.  That condition can be CHECKED exactly, so a round works on a
+// whole window of pending collisions at once:
+//
+//   1. post      every ball owner whose candidate key (time, code) lies below the window end `theta` posts it;
+//                one grid barrier later every CTA holds the same complete list of keys < theta, sorts it and
+//                cuts it at the first entry that shares a ball with an earlier one (or is only a lower bound);
+//   2. resolve   one thread per listed collision computes the new velocities (elastic_collision / obstacle);
+//   3. solve     every owner solves its pair with every ball of the batch -- with its state as of just before
+//                that collision -- and parks the values in shared memory; any new key that would come earlier
+//                than a collision of the batch is a violation;
+//   4. commit    the batch prefix below the earliest violation (all of it, normally) is committed: table rows
+//                and columns stored, candidates folded, states updated, log written.  The rest is re-posted.
+//
+// Collision 1 of a round is the true global minimum, so every round commits at least what the reference's
+// iteration would; the committed sequence, every table entry and every state bit are the reference's.
+//
+// Data placement: a ball is owned by one thread; its state of record (p0, v, t0) and candidate keys live in
+// that thread's registers for the whole launch (mirrored to global memory when they change, so that resolvers
+// can read any ball); the symmetric table of absolute impact times stays in HBM and is only written (row of
+// the colliding ball: coalesced; column: strided) -- it is read again only to repair a stale candidate.
+// Grid: ceil(N/T) CTAs, one per SM; <= 16 CTAs run as one thread-block cluster (hardware barrier), more use a
+// cooperative launch with a global-memory barrier.
 //
 // "Cover" instead of row minima: ball k's candidate m[k] is the minimum over a SUBSET of row k that
 // always contains every pair whose value was last written at an event of the OTHER ball.  After an event of ball
-// a every pair (a,k) is re-solved and folded into m[k] by k's owner, so m[a] can simply be emptied -- no
-// cross-thread reduction for the rows of the colliding balls.  If k's candidate was its pair with a and the new
-// value is larger, m[k] keeps the old time as a lower bound ("stale"); stale rows are re-read from the table only
-// when one of them wins the argmin, all stale rows of the cluster at once (bandwidth-bound, amortised).
-// The global minimum over {m[k]} equals the minimum over the whole table, so the committed event order is the
-// reference's, bit for bit.
+// a every pair (a,k) is re-solved and folded into m[k] by k's owner, so m[a] is simply emptied.  If k's
+// candidate was its pair with a and the new value is larger, m[k] keeps the old time as a lower bound ("stale");
+// stale rows are re-read from the table only when one of them reaches the front of the queue.  The global
+// minimum over {m[k]} equals the minimum over the whole table.
 #include <cstdio>
 
 #include "bl_arith.cuh"
@@ -30,33 +47,12 @@
 
 namespace {
 
-// ---- per-ball fields resident in shared memory: fd[F_*][cap] doubles, then u64 / int arrays ----------
-enum {
-    F_P0X = 0, F_P0Y, F_VX, F_VY, F_T0, F_MASS,          // state of record of the ball (payload words 2..7)
-    F_QP0X, F_QP0Y, F_QVX, F_QVY, F_QT0, F_QMASS,        // cached state of the candidate's partner (words 8..13)
-    F_OARG,                                              // obstacle arg (word 16)
-    F_MT, F_OT, F_RADIUS,
-    NFD
-};
-enum { I_RC = 0, I_QRC, I_OIDX, NFI };
+enum { MODE_WINDOW = 0, MODE_ARGMIN = 1 };
+enum { KIND_BOTH = 0, KIND_BB = 1, KIND_BO = 2 };
+enum { SYNC_CTA = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
 
-// payload exchanged between CTAs (8-byte words)
-enum {
-    W_TS = 0, W_CODE, W_K0 = 2, W_Q0 = 8, W_INT0 = 14, W_INT1 = 15, W_OARG = 16, NW = 17, NW_PAD = 18
-};
-
-enum { EV_STOP = 0, EV_BB = 1, EV_BO = 2, EV_RESCAN = 3 };
-enum { MODE_BOTH = 0, MODE_BB = 1, MODE_BO = 2 };
-
-struct Bcast {
-    double t;
-    int kind, a, b, rca, rcb, status, stop, obs;
-    double ax, ay, avx, avy, amass;  // ball a after the event (position = new p0, t0 = t)
-    double bx, by, bvx, bvy, bmass;
-    uint64_t ts, code;
-    double q_arg;
-    int k, pad;
-};
+// flags of a collected entry
+enum { F_DUP = 1, F_CONFLICT = 2, F_STALE = 4 };
 
 struct Params {
     bl_system s;
@@ -66,31 +62,83 @@ struct Params {
     int query_only;
     bl_log log;
     bl_result *result;
-    int cap;   // balls per CTA
-    int bpt;   // balls per thread
+    int T;          // threads per CTA = balls per CTA
+    int ncta;
+    int m_max;      // collisions per round the stash has room for
+    int target;     // collisions per round the window aims at
+    int sync_mode;
+    double window;  // initial window length (0: unknown)
+    unsigned *bar;  // grid barrier counter (zero at launch)
+    uint64_t *post; // [2][BL_MAX_CTAS][BL_POST_WORDS]
+    uint64_t *viol; // [2][BL_MAX_CTAS]
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
+// ---- shared memory map (8-byte words) -----------------------------------------------------------------
+struct Layout {
+    int stash;                        // [2*m_max][T] doubles
+    int bx, by, bvx, bvy, bt;         // [2*m_max] batch balls: state right after their collision
+    int bid, brc;                     // [2*m_max] ints: ball index (-1: none), radius class
+    int e_ts, e_code;                 // [BL_EV_CAP] collected keys (unsorted)
+    int s_ts, s_code, s_flag;         // [BL_EV_CAP] sorted keys, flags (int)
+    int r_pay;                        // [m_max][13] log payload per rank
+    int r_info;                       // [m_max][4] ints: status, obstacle index, is ball-ball, pad
+    int pl_ts, pl_code;               // [BL_R_POST] this CTA's posted keys
+    int w_ts, w_code;                 // [32] warp slots of the exact argmin
+    int mass, radius, oarg;           // [T] doubles
+    int oidx, brank;                  // [T] ints
+    int dirty;                        // [T] ints
+    int scratch;                      // [2*T] repair results (ts, code) / new obstacle entry
+    int obs;                          // 5 * n_obs
+    int misc;                         // 32 words
+    int words;
+};
+__host__ __device__ inline Layout make_layout(int T, int m_max, int n_obs) {
+    Layout L;
+    int w = 0;
+    L.stash = w; w += 2 * m_max * T;
+    L.bx = w; w += 2 * m_max; L.by = w; w += 2 * m_max; L.bvx = w; w += 2 * m_max; L.bvy = w; w += 2 * m_max;
+    L.bt = w; w += 2 * m_max;
+    L.bid = w; w += m_max; L.brc = w; w += m_max;
+    L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP;
+    L.s_ts = w; w += BL_EV_CAP; L.s_code = w; w += BL_EV_CAP; L.s_flag = w; w += BL_EV_CAP / 2;
+    L.r_pay = w; w += 13 * m_max;
+    L.r_info = w; w += 2 * m_max;
+    L.pl_ts = w; w += BL_R_POST; L.pl_code = w; w += BL_R_POST;
+    L.w_ts = w; w += 32; L.w_code = w; w += 32;
+    L.mass = w; w += T; L.radius = w; w += T; L.oarg = w; w += T;
+    L.oidx = w; w += (T + 1) / 2; L.brank = w; w += (T + 1) / 2;
+    L.dirty = w; w += (T + 1) / 2;
+    L.scratch = w; w += 2 * T;
+    L.obs = w; w += 5 * (n_obs > 0 ? n_obs : 1);
+    L.misc = w; w += 32;
+    L.words = w;
+    return L;
 }
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_u64(uint32_t addr, uint64_t v) {
-    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
-}
+// ints of `misc`; M_VIOL is a 64-bit word index
+enum { M_PCOUNT = 0, M_ECOUNT, M_OVERFLOW, M_CUT, M_NDIRTY, M_ERRRANK };
+enum { M_VIOL = 8 };
+
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all CTAs of the launch; global-memory writes made before it are visible to ld.cg after it
+__device__ __forceinline__ void sync_all(const Params &P, unsigned &epoch) {
+    if (P.sync_mode == SYNC_CTA) { __syncthreads(); return; }
+    if (P.sync_mode == SYNC_CLUSTER) { cluster_sync_all(); return; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += (unsigned)P.ncta;
+        __threadfence();
+        atomicAdd(P.bar, 1u);
+        while ((int)(ld_acquire_u32(P.bar) - epoch) < 0) {}
+    }
+    __syncthreads();
 }
 
 // lane holding the lexicographically smallest (ts, code); 4 REDUX + 1 ballot
@@ -111,468 +159,641 @@ __device__ __forceinline__ int warp_argmin(uint64_t ts, uint64_t code) {
     unsigned b = __ballot_sync(FULL, c);
     return __ffs(b) - 1;
 }
-
-struct Smem {
-    double *fd;        // [NFD][cap]
-    uint64_t *mcode;   // [cap]
-    int *fi;           // [NFI][cap]
-    int *dirty;        // [cap]
-    bl_obstacle *obs;  // [n_obs]
-    uint64_t *slots;   // [32][4]  (ts, code, local ball, pad)
-    uint64_t *inbox;   // [2][16][NW_PAD]
-    Bcast *bc;
-    int *n_dirty;
-    int cap;
-    __device__ __forceinline__ double &d(int f, int k) const { return fd[f * cap + k]; }
-    __device__ __forceinline__ int &i(int f, int k) const { return fi[f * cap + k]; }
-};
-
-__host__ __device__ inline size_t smem_bytes(int cap, int n_obs) {
-    size_t b = 0;
-    b += (size_t)NFD * cap * 8;
-    b += (size_t)cap * 8;
-    b += (size_t)NFI * cap * 4;
-    b += (size_t)cap * 4;
-    b = (b + 15) & ~(size_t)15;
-    b += (size_t)(n_obs > 0 ? n_obs : 1) * sizeof(bl_obstacle);
-    b += 32 * 4 * 8;
-    b += 2 * 16 * NW_PAD * 8;
-    b += sizeof(Bcast) + 16;
-    b += 16;
-    return b;
+// minimum of a 64-bit value over the warp (two REDUX)
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned hi = __reduce_min_sync(FULL, (unsigned)(v >> 32));
+    const unsigned lo = __reduce_min_sync(FULL, (unsigned)(v >> 32) == hi ? (unsigned)v : 0xffffffffu);
+    return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ Smem carve(unsigned char *raw, int cap, int n_obs) {
-    Smem m;
-    m.cap = cap;
-    unsigned char *p = raw;
-    m.fd = (double *)p; p += (size_t)NFD * cap * 8;
-    m.mcode = (uint64_t *)p; p += (size_t)cap * 8;
-    m.fi = (int *)p; p += (size_t)NFI * cap * 4;
-    m.dirty = (int *)p; p += (size_t)cap * 4;
-    p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    m.obs = (bl_obstacle *)p; p += (size_t)(n_obs > 0 ? n_obs : 1) * sizeof(bl_obstacle);
-    m.slots = (uint64_t *)p; p += 32 * 4 * 8;
-    m.inbox = (uint64_t *)p; p += 2 * 16 * NW_PAD * 8;
-    m.bc = (Bcast *)p; p += (sizeof(Bcast) + 15) & ~(size_t)15;
-    m.n_dirty = (int *)p;
-    return m;
+__device__ __forceinline__ double as_d(uint64_t u) { return __longlong_as_double((long long)u); }
+__device__ __forceinline__ uint64_t as_u(double d) { return (uint64_t)__double_as_longlong(d); }
+__device__ __forceinline__ uint64_t pack2(int lo, int hi) { return (uint64_t)(unsigned)lo | ((uint64_t)(unsigned)hi << 32); }
+__device__ __forceinline__ int lo32(uint64_t u) { return (int)(u & 0xffffffffu); }
+__device__ __forceinline__ int hi32(uint64_t u) { return (int)(u >> 32); }
+
+// balls of a key: pair -> (lo, hi); obstacle hit -> (ball, -1); stale / none -> (-1, -1)
+__device__ __forceinline__ void key_balls(uint64_t code, int &a, int &b) {
+    if (code == BL_CODE_STALE || code == BL_CODE_NONE || code == BL_CODE_END) { a = -1; b = -1; }
+    else if (code & BL_CODE_OBS) { a = (int)(code & 0x7fffffffull); b = -1; }
+    else { a = bl_code_lo(code); b = bl_code_hi(code); }
 }
 
-// ---------------------------------------------------------------------------------------------
-template <bool FMA>
-__global__ void __launch_bounds__(BL_MAX_THREADS, 1) bl_evolve_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const bl_system &S = P.s;
-    const int n = S.n, K = S.n_classes, n_obs = S.n_obstacles;
-    const size_t pitch = (size_t)S.pitch;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int rank = (int)cluster_ctarank(), C = (int)cluster_nctarank();
-    const int cap = P.cap, bpt = P.bpt;
-    const Smem M = carve(smem_raw, cap, n_obs);
-    Bcast &bc = *M.bc;
-
-    // ball owned by (rank, tid, slot u): local index kl = u*nthreads + tid, global index k = rank*cap + kl
-    const int kbase = rank * cap;
-
-    // ---- load the resident state --------------------------------------------------------------
-    for (int q = tid; q < n_obs; q += nthreads) M.obs[q] = S.obstacles[q];
-    for (int u = 0; u < bpt; u++) {
-        const int kl = u * nthreads + tid, k = kbase + kl;
-        if (k < n) {
-            M.d(F_P0X, kl) = S.p0x[k]; M.d(F_P0Y, kl) = S.p0y[k];
-            M.d(F_VX, kl) = S.vx[k];   M.d(F_VY, kl) = S.vy[k];
-            M.d(F_T0, kl) = S.t0[k];   M.d(F_MASS, kl) = S.mass[k];
-            M.d(F_RADIUS, kl) = S.radius[k];
-            M.i(I_RC, kl) = S.rclass[k];
-            M.d(F_OT, kl) = S.obs_t[k]; M.i(I_OIDX, kl) = S.obs_idx[k]; M.d(F_OARG, kl) = S.obs_arg[k];
-            const double mt = S.cover_t[k];
-            const uint64_t mc = S.cover_code[k];
-            M.d(F_MT, kl) = mt; M.mcode[kl] = mc;
-            int q = -1;
-            if (mc != BL_CODE_STALE && mc != BL_CODE_NONE) q = bl_code_hi(mc) == k ? bl_code_lo(mc) : bl_code_hi(mc);
-            if (q >= 0) {
-                M.d(F_QP0X, kl) = S.p0x[q]; M.d(F_QP0Y, kl) = S.p0y[q];
-                M.d(F_QVX, kl) = S.vx[q];   M.d(F_QVY, kl) = S.vy[q];
-                M.d(F_QT0, kl) = S.t0[q];   M.d(F_QMASS, kl) = S.mass[q];
-                M.i(I_QRC, kl) = S.rclass[q];
-            } else {
-                M.d(F_QP0X, kl) = 0; M.d(F_QP0Y, kl) = 0; M.d(F_QVX, kl) = 0; M.d(F_QVY, kl) = 0;
-                M.d(F_QT0, kl) = 0; M.d(F_QMASS, kl) = 0; M.i(I_QRC, kl) = 0;
+// minimum of table row dk (all n entries, 8 loads in flight per lane) -> (ts, code) in out[0..1]
+__device__ __noinline__ void rescan_row(const double *__restrict__ row, int n, int dk, int lane, uint64_t *out) {
+    uint64_t ts = ~0ull, cd = BL_CODE_END;
+    for (int x0 = 0; x0 < n; x0 += 256) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int x = x0 + u * 32 + lane;
+            v[u] = x < n ? __ldcg(row + x) : BL_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int x = x0 + u * 32 + lane;
+            if (v[u] < BL_INF && x != dk) {
+                const uint64_t s2 = bl_sortable(v[u]), c2 = bl_pair_code(dk, x);
+                if (bl_key_less(s2, c2, ts, cd)) { ts = s2; cd = c2; }
             }
         }
     }
-    if (tid == 0) *M.n_dirty = 0;
+    const int w = warp_argmin(ts, cd);
+    ts = __shfl_sync(0xffffffffu, ts, w);
+    cd = __shfl_sync(0xffffffffu, cd, w);
+    if (lane == 0) {
+        if (cd == BL_CODE_END) { out[0] = bl_sortable(BL_INF); out[1] = BL_CODE_NONE; }
+        else { out[0] = ts; out[1] = cd; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool FMA, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) uint64_t sm[];
+    const bl_system &S = P.s;
+    const int n = S.n, K = S.n_classes, n_obs = S.n_obstacles;
+    const int T = P.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int cta = blockIdx.x, ncta = P.ncta, m_max = P.m_max;
+    const Layout L = make_layout(T, m_max, n_obs);
+    double *stash = reinterpret_cast<double *>(sm + L.stash);
+    double *bx = reinterpret_cast<double *>(sm + L.bx), *by = reinterpret_cast<double *>(sm + L.by);
+    double *bvx = reinterpret_cast<double *>(sm + L.bvx), *bvy = reinterpret_cast<double *>(sm + L.bvy);
+    double *bt = reinterpret_cast<double *>(sm + L.bt);
+    int *bid = reinterpret_cast<int *>(sm + L.bid), *brc = reinterpret_cast<int *>(sm + L.brc);
+    uint64_t *e_ts = sm + L.e_ts, *e_code = sm + L.e_code, *s_ts = sm + L.s_ts, *s_code = sm + L.s_code;
+    int *s_flag = reinterpret_cast<int *>(sm + L.s_flag);
+    double *r_pay = reinterpret_cast<double *>(sm + L.r_pay);
+    int *r_info = reinterpret_cast<int *>(sm + L.r_info);
+    uint64_t *pl_ts = sm + L.pl_ts, *pl_code = sm + L.pl_code, *w_ts = sm + L.w_ts, *w_code = sm + L.w_code;
+    double *c_mass = reinterpret_cast<double *>(sm + L.mass), *c_radius = reinterpret_cast<double *>(sm + L.radius);
+    double *c_oarg = reinterpret_cast<double *>(sm + L.oarg);
+    int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *brank = reinterpret_cast<int *>(sm + L.brank);
+    int *dirty = reinterpret_cast<int *>(sm + L.dirty);
+    uint64_t *scratch = sm + L.scratch;
+    const bl_obstacle *obs = reinterpret_cast<const bl_obstacle *>(sm + L.obs);
+    int *misc = reinterpret_cast<int *>(sm + L.misc);
+    unsigned long long *m_viol = reinterpret_cast<unsigned long long *>(sm + L.misc + M_VIOL);
+
+    const int base = cta * T;
+    const int k = base + tid;  // the ball this thread owns
+    const bool own = k < n;
+
+    // ---- load the resident state --------------------------------------------------------------
+    for (int q = tid; q < 5 * n_obs; q += T) sm[L.obs + q] = reinterpret_cast<const uint64_t *>(S.obstacles)[q];
+    double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0;
+    uint64_t mts = bl_sortable(BL_INF), mcode = BL_CODE_NONE, ots = bl_sortable(BL_INF);
+    int myrc = 0;
+    if (own) {
+        p0x = S.p0x[k]; p0y = S.p0y[k]; vx = S.vx[k]; vy = S.vy[k]; t0 = S.t0[k];
+        myrc = S.rclass[k];
+        c_mass[tid] = S.mass[k];
+        c_radius[tid] = S.radius[k];
+        c_oarg[tid] = S.obs_arg[k];
+        c_oidx[tid] = S.obs_idx[k];
+        ots = bl_sortable(S.obs_t[k]);
+        mts = bl_sortable(S.cover_t[k]);
+        mcode = S.cover_code[k];
+    }
+    brank[tid] = -1;
+    const double rs11 = (K == 1 && n > 0) ? S.rsum2[0] : 0.0;
+    double *const myrow = S.toi + (size_t)(own ? k : 0) * (size_t)S.pitch;
+    if (tid < 32) sm[L.misc + tid] = 0;
     __syncthreads();
-    cluster_sync_all();  // every CTA's shared memory is live before anybody writes into an inbox
+    if (tid == 0) { misc[M_CUT] = BL_EV_CAP; misc[M_ERRRANK] = BL_EV_CAP; *m_viol = ~0ull; }
 
-    long long n_bb = 0, n_bo = 0, n_logged = 0, n_rescans = 0;
-    double now = P.time;
-    int mode = P.first_kind == BL_BALL_BALL ? MODE_BB : (P.first_kind == BL_BALL_OBSTACLE ? MODE_BO : MODE_BOTH);
-    int parity = 0;
-    int final_stage = P.query_only ? 1 : 0;  // 0: event loop, 1: report next ball-ball, 2: report next ball-obstacle
-    int stop = BL_STOP_TIME, status = BL_OK;
-    long long err_i = -1, err_j = -1;
-    double bb_t = BL_INF, bo_t = BL_INF, bo_arg = 0.0;
-    long long bb_i = -1, bb_j = 0, bo_ball = -1, bo_obs = -1;
-    if (final_stage == 1) mode = MODE_BB;
-
+    const bool prof_thread = tid == 0;
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (;;) {
-        const long long c0 = clock64();
-        prof[5]++;
-        // ---- argmin, thread level: best candidate among the owned balls ----------------------------
-        uint64_t best_ts = ~0ull, best_code = BL_CODE_END;
-        int best_kl = 0;
-        for (int u = 0; u < bpt; u++) {
-            const int kl = u * nthreads + tid, k = kbase + kl;
-            if (k >= n) continue;
-            if (mode != MODE_BO) {
-                const uint64_t ts = bl_sortable(M.d(F_MT, kl)), cd = M.mcode[kl];
-                if (bl_key_less(ts, cd, best_ts, best_code)) { best_ts = ts; best_code = cd; best_kl = kl; }
-            }
-            if (mode != MODE_BB) {
-                const uint64_t ts = bl_sortable(M.d(F_OT, kl)), cd = BL_CODE_OBS | (uint64_t)k;
-                if (bl_key_less(ts, cd, best_ts, best_code)) { best_ts = ts; best_code = cd; best_kl = kl; }
-            }
-        }
-        // ---- warp level ---------------------------------------------------------------------------
-        {
-            const int w = warp_argmin(best_ts, best_code);
-            if (lane == w) {
-                M.slots[warp * 4 + 0] = best_ts; M.slots[warp * 4 + 1] = best_code;
-                M.slots[warp * 4 + 2] = (uint64_t)best_kl;
-            }
-        }
-        __syncthreads();
-        // ---- CTA level: warp 0 picks the CTA winner and posts its payload into every CTA's inbox -------
-        if (warp == 0) {
-            uint64_t ts = ~0ull, cd = BL_CODE_END;
-            if (lane < nwarps) { ts = M.slots[lane * 4 + 0]; cd = M.slots[lane * 4 + 1]; }
-            const int w = warp_argmin(ts, cd);
-            const int kl = (int)M.slots[w * 4 + 2];
-            uint64_t word = 0;
-            if (lane == W_TS) word = M.slots[w * 4 + 0];
-            else if (lane == W_CODE) word = M.slots[w * 4 + 1];
-            else if (lane < W_INT0) word = (uint64_t)__double_as_longlong(M.fd[(lane - W_K0) * cap + kl]);
-            else if (lane == W_INT0) word = ((uint64_t)(unsigned)(kbase + kl) << 32) | (unsigned)M.i(I_RC, kl);
-            else if (lane == W_INT1) word = ((uint64_t)(unsigned)M.i(I_QRC, kl) << 32) | (unsigned)M.i(I_OIDX, kl);
-            else if (lane == W_OARG) word = (uint64_t)__double_as_longlong(M.d(F_OARG, kl));
-            if (lane < NW) {
-                const uint32_t local = smem_u32(&M.inbox[(parity * 16 + rank) * NW_PAD + lane]);
-                for (int c = 0; c < C; c++) st_cluster_u64(mapa(local, (uint32_t)c), word);
-            }
-        }
-        cluster_sync_all();
-        const long long c1 = clock64();
-        prof[0] += c1 - c0;
-        // ---- cluster level + resolve: warp 0 of every CTA redundantly --------------------------------
-        if (warp == 0) {
-            const uint64_t *box = &M.inbox[parity * 16 * NW_PAD];
-            uint64_t ts = ~0ull, cd = BL_CODE_END;
-            if (lane < C) { ts = box[lane * NW_PAD + W_TS]; cd = box[lane * NW_PAD + W_CODE]; }
-            const int cw = warp_argmin(ts, cd);
-            const uint64_t *w = &box[cw * NW_PAD];
-            ts = w[W_TS]; cd = w[W_CODE];
-            const double t = bl_unsortable(ts);
-            int kind = EV_STOP, st_local = BL_OK, stop_local = BL_STOP_TIME;
-            const int k = (int)(w[W_INT0] >> 32), krc = (int)(w[W_INT0] & 0xffffffffu);
-            const int qrc = (int)(w[W_INT1] >> 32), oidx = (int)(w[W_INT1] & 0xffffffffu);
-            const long long events = n_bb + n_bo;
-            if (cd == BL_CODE_STALE) {
-                kind = EV_RESCAN;
-            } else if (final_stage) {
-                kind = EV_STOP;
-            } else if (cd == BL_CODE_NONE || cd == BL_CODE_END) {
-                kind = EV_STOP;
-                stop_local = (P.max_events >= 0 && events >= P.max_events) ? BL_STOP_EVENTS : BL_STOP_TIME;
-            } else if (ts == BL_TS_NAN) {
-                kind = EV_STOP; st_local = BL_ENAN; stop_local = BL_STOP_ERROR;
-            } else if (P.max_events >= 0 && events >= P.max_events) {
-                kind = EV_STOP; stop_local = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
-            } else if (!(t <= P.end_time) || t == BL_INF) {
-                kind = EV_STOP; stop_local = BL_STOP_TIME;
-            } else if (P.log.cap > 0 && n_logged >= P.log.cap) {
-                kind = EV_STOP; stop_local = BL_STOP_LOG;
-            } else if (cd & BL_CODE_OBS) {
-                // ---- ball-obstacle, simulation.py:504-519 + :604-636 ----
-                kind = EV_BO;
-                const double p0x = __longlong_as_double(w[W_K0 + 0]), p0y = __longlong_as_double(w[W_K0 + 1]);
-                const double vx = __longlong_as_double(w[W_K0 + 2]), vy = __longlong_as_double(w[W_K0 + 3]);
-                const double t0 = __longlong_as_double(w[W_K0 + 4]);
-                const double arg = __longlong_as_double(w[W_OARG]);
-                const double px = bl_advance(p0x, vx, t, t0), py = bl_advance(p0y, vy, t, t0);
-                double wx = 0, wy = 0;
-                st_local = bl_obstacle_bounce<FMA>(M.obs[oidx], px, py, vx, vy, arg, wx, wy);
-                if (st_local != BL_OK) { kind = EV_STOP; stop_local = BL_STOP_ERROR; }
-                if (lane == 0) {
-                    bc.a = k; bc.b = -1; bc.rca = krc; bc.rcb = 0; bc.obs = oidx;
-                    bc.ax = px; bc.ay = py; bc.avx = wx; bc.avy = wy; bc.amass = __longlong_as_double(w[W_K0 + 5]);
-                    bc.q_arg = arg;
-                    if (kind == EV_BO && rank == 0 && P.log.cap > 0) {
-                        const long long e = n_logged;
-                        P.log.t[e] = t; P.log.i[e] = k; P.log.j[e] = -1 - (long long)oidx;
-                        if (P.log.payload) {
-                            double *pl = P.log.payload + 12 * e;
-                            pl[0] = px; pl[1] = py; pl[2] = vx; pl[3] = vy; pl[4] = wx; pl[5] = wy; pl[6] = arg;
-                            pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0;
-                        }
-                    }
-                }
-            } else {
-                // ---- ball-ball, simulation.py:446-455 + :562-602 ----
-                kind = EV_BB;
-                const int hi = bl_code_hi(cd), lo = bl_code_lo(cd);
-                // the publisher is ball k, its cached partner is the other one; a = smaller index (idx1 < idx2)
-                const bool k_is_a = (k == lo);
-                const uint64_t *wa = k_is_a ? &w[W_K0] : &w[W_Q0];
-                const uint64_t *wb = k_is_a ? &w[W_Q0] : &w[W_K0];
-                const double a_p0x = __longlong_as_double(wa[0]), a_p0y = __longlong_as_double(wa[1]);
-                const double a_vx = __longlong_as_double(wa[2]), a_vy = __longlong_as_double(wa[3]);
-                const double a_t0 = __longlong_as_double(wa[4]), a_m = __longlong_as_double(wa[5]);
-                const double b_p0x = __longlong_as_double(wb[0]), b_p0y = __longlong_as_double(wb[1]);
-                const double b_vx = __longlong_as_double(wb[2]), b_vy = __longlong_as_double(wb[3]);
-                const double b_t0 = __longlong_as_double(wb[4]), b_m = __longlong_as_double(wb[5]);
-                const double ax = bl_advance(a_p0x, a_vx, t, a_t0), ay = bl_advance(a_p0y, a_vy, t, a_t0);
-                const double bx = bl_advance(b_p0x, b_vx, t, b_t0), by = bl_advance(b_p0y, b_vy, t, b_t0);
-                double m1 = a_m, m2 = b_m;
-                bl_remap_masses(m1, m2);
-                double w1x = 0, w1y = 0, w2x = 0, w2y = 0;
-                st_local = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bx, by, b_vx, b_vy, m2, w1x, w1y, w2x, w2y);
-                if (st_local != BL_OK) { kind = EV_STOP; stop_local = BL_STOP_ERROR; }
-                if (lane == 0) {
-                    bc.a = lo; bc.b = hi;
-                    bc.rca = k_is_a ? krc : qrc; bc.rcb = k_is_a ? qrc : krc; bc.obs = -1;
-                    bc.ax = ax; bc.ay = ay; bc.avx = w1x; bc.avy = w1y; bc.amass = a_m;
-                    bc.bx = bx; bc.by = by; bc.bvx = w2x; bc.bvy = w2y; bc.bmass = b_m;
-                    if (kind == EV_BB && rank == 0 && P.log.cap > 0) {
-                        const long long e = n_logged;
-                        P.log.t[e] = t; P.log.i[e] = lo; P.log.j[e] = hi;
-                        if (P.log.payload) {
-                            double *pl = P.log.payload + 12 * e;
-                            pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = w1x; pl[5] = w1y;
-                            pl[6] = bx; pl[7] = by; pl[8] = b_vx; pl[9] = b_vy; pl[10] = w2x; pl[11] = w2y;
-                        }
-                    }
-                }
-            }
-            if (lane == 0) {
-                bc.t = t; bc.kind = kind; bc.status = st_local; bc.stop = stop_local; bc.ts = ts; bc.code = cd;
-                bc.k = k;
-                if (kind == EV_STOP && (cd & BL_CODE_OBS) && cd != BL_CODE_END) {
-                    bc.obs = oidx; bc.q_arg = __longlong_as_double(w[W_OARG]);
-                }
-            }
-        }
-        parity ^= 1;
-        __syncthreads();
-        const long long c2 = clock64();
-        prof[1] += c2 - c1;
+    long long done = 0, n_bb = 0, n_rescans = 0;
+    double now = P.time;   // Billiard.time: time of the last committed collision
+    double prev_now = P.time;
+    double win = P.window;
+    int mode = (P.first_kind != BL_ANY || P.query_only || !(win > 0.0)) ? MODE_ARGMIN : MODE_WINDOW;
+    int kindmask = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
+    int final_stage = P.query_only ? 1 : 0;  // 0: event loop, 1: report next ball-ball, 2: report next ball-obstacle
+    if (final_stage == 1) kindmask = KIND_BB;
+    int shrinks = 0;
+    unsigned par = 0, epoch = 0;
+    const bool want_log = P.log.cap > 0;
+    bl_result *const res = P.result;
+    // exclusive upper bound of the keys that may be processed: t <= end_time and t < inf
+    const uint64_t ts_inf = bl_sortable(BL_INF);
+    uint64_t end_excl = bl_sortable(P.end_time);
+    end_excl = end_excl >= ts_inf ? ts_inf : end_excl + 1;
+    __syncthreads();
+    if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 
-        const int kind = bc.kind;
-        if (kind == EV_RESCAN) {
-            // ---- repair every stale candidate of this CTA from the table (one warp per row) -------------
-            for (int u = 0; u < bpt; u++) {
-                const int kl = u * nthreads + tid;
-                if (kbase + kl < n && M.mcode[kl] == BL_CODE_STALE) M.dirty[atomicAdd(M.n_dirty, 1)] = kl;
+    for (;;) {
+        long long c0 = 0;
+        if (prof_thread) { c0 = clock64(); prof[5]++; }
+        // =========================== 1. post =================================================================
+        uint64_t theta = 0;
+        if (mode == MODE_WINDOW) {
+            theta = bl_sortable(bl_add(now, win));
+            if (theta > end_excl) theta = end_excl;
+        }
+        uint64_t kts = ~0ull, kcode = BL_CODE_END;
+        if (own) {
+            if (kindmask != KIND_BO) { kts = mts; kcode = mcode; }
+            if (kindmask != KIND_BB) {
+                const uint64_t oc = BL_CODE_OBS | (uint64_t)k;
+                if (kindmask == KIND_BO || bl_key_less(ots, oc, kts, kcode)) { kts = ots; kcode = oc; }
+            }
+        }
+        if (mode == MODE_WINDOW) {
+            if (own && kts < theta) {
+                const int s = atomicAdd(&misc[M_PCOUNT], 1);
+                if (s < BL_R_POST) { pl_ts[s] = kts; pl_code[s] = kcode; }
             }
             __syncthreads();
-            const int nd = *M.n_dirty;
-            for (int d = warp; d < nd; d += nwarps) {
-                const int kl = M.dirty[d], k = kbase + kl;
-                const double *row = S.toi + (size_t)k * pitch;
+        } else {
+            const int w = warp_argmin(kts, kcode);
+            if (lane == w) { w_ts[warp] = kts; w_code[warp] = kcode; }
+            __syncthreads();
+            if (warp == 0) {
                 uint64_t ts = ~0ull, cd = BL_CODE_END;
-                for (int x = lane; x < n; x += 32) {
-                    const double v = __ldcg(row + x);
-                    if (x != k && v < BL_INF) {
-                        const uint64_t s2 = bl_sortable(v), c2 = bl_pair_code(k, x);
-                        if (bl_key_less(s2, c2, ts, cd)) { ts = s2; cd = c2; }
-                    }
-                }
-                const int w = warp_argmin(ts, cd);
-                ts = __shfl_sync(0xffffffffu, ts, w);
-                cd = __shfl_sync(0xffffffffu, cd, w);
-                if (lane == 0) {
-                    if (cd == BL_CODE_END) {
-                        M.d(F_MT, kl) = BL_INF; M.mcode[kl] = BL_CODE_NONE;
-                    } else {
-                        const int q = bl_code_hi(cd) == k ? bl_code_lo(cd) : bl_code_hi(cd);
-                        M.d(F_MT, kl) = bl_unsortable(ts); M.mcode[kl] = cd;
-                        M.d(F_QP0X, kl) = __ldcg(S.p0x + q); M.d(F_QP0Y, kl) = __ldcg(S.p0y + q);
-                        M.d(F_QVX, kl) = __ldcg(S.vx + q);   M.d(F_QVY, kl) = __ldcg(S.vy + q);
-                        M.d(F_QT0, kl) = __ldcg(S.t0 + q);   M.d(F_QMASS, kl) = S.mass[q];
-                        M.i(I_QRC, kl) = S.rclass[q];
-                    }
+                if (lane < nwarps) { ts = w_ts[lane]; cd = w_code[lane]; }
+                const int w2 = nwarps > 1 ? warp_argmin(ts, cd) : 0;
+                if (lane == w2) { pl_ts[0] = ts; pl_code[0] = cd; misc[M_PCOUNT] = cd != BL_CODE_END ? 1 : 0; }
+            }
+            __syncthreads();
+        }
+        if (tid <= 2 * BL_R_POST) {
+            uint64_t *const post = P.post + ((size_t)par * BL_MAX_CTAS + cta) * BL_POST_WORDS;
+            const int pc = misc[M_PCOUNT];
+            uint64_t word;
+            if (tid == 0) word = pack2(pc < BL_R_POST ? pc : BL_R_POST, pc > BL_R_POST ? 1 : 0);
+            else word = (tid & 1) ? pl_ts[(tid - 1) >> 1] : pl_code[(tid - 1) >> 1];
+            __stcg(post + tid, word);
+        }
+        sync_all(P, epoch);
+        // =========================== 2. collect ==============================================================
+        {
+            const uint64_t *const box = P.post + (size_t)par * BL_MAX_CTAS * BL_POST_WORDS;
+            for (int c = tid; c < ncta; c += T) {
+                const uint64_t *rec = box + (size_t)c * BL_POST_WORDS;
+                const uint64_t hd = __ldcg(rec);
+                const int cnt = lo32(hd);
+                if (hi32(hd)) misc[M_OVERFLOW] = 1;
+                for (int e = 0; e < cnt; e++) {
+                    const int slot = atomicAdd(&misc[M_ECOUNT], 1);
+                    if (slot < BL_EV_CAP) { e_ts[slot] = __ldcg(rec + 1 + 2 * e); e_code[slot] = __ldcg(rec + 2 + 2 * e); }
+                    else misc[M_OVERFLOW] = 1;
                 }
             }
-            n_rescans += nd;  // per-CTA count; summed over CTAs at the end
+        }
+        par ^= 1;
+        __syncthreads();
+        const int nE = misc[M_ECOUNT];
+        const bool overflow = misc[M_OVERFLOW] != 0;
+        __syncthreads();
+        if (tid == 0) { misc[M_PCOUNT] = 0; misc[M_ECOUNT] = 0; misc[M_OVERFLOW] = 0; }
+        if (overflow) {  // too many keys below theta: halve the window and post again (nothing has changed)
+            win = bl_mul(win, 0.5);
+            if (++shrinks >= 6) mode = MODE_ARGMIN;
+            if (prof_thread) { prof[7]++; prof[0] += clock64() - c0; }
             __syncthreads();
-            if (tid == 0) *M.n_dirty = 0;
-            prof[3] += clock64() - c2;
-            prof[4]++;
             continue;
         }
-        if (kind == EV_STOP) {
+        shrinks = 0;
+
+        // what this round turns out to be
+        int stop_kind = -1, st_status = BL_OK;  // stop_kind >= 0: leave the event loop with this bl_stop
+        int nf = 0;                              // collisions handed to resolve
+        bool repair = false;
+        const bool max_reached = P.max_events >= 0 && done >= P.max_events;
+        if (nE == 0) {
+            if (final_stage == 0 && !max_reached && mode == MODE_WINDOW && theta < end_excl) {
+                mode = MODE_ARGMIN;  // empty window: find the true minimum
+                win = bl_mul(win, 2.0);
+                if (prof_thread) { prof[7]++; prof[0] += clock64() - c0; }
+                __syncthreads();
+                continue;
+            }
+            stop_kind = max_reached ? BL_STOP_EVENTS : BL_STOP_TIME;  // nothing pending at or before end_time
+        } else {
+            // ---- sort by (ts, code, slot): rank by counting ----
+            for (int i = tid; i < nE; i += T) {
+                const uint64_t ts = e_ts[i], cd = e_code[i];
+                int r = 0;
+                for (int j = 0; j < nE; j++) {
+                    const uint64_t t2 = e_ts[j], c2 = e_code[j];
+                    r += (bl_key_less(t2, c2, ts, cd) || (t2 == ts && c2 == cd && j < i)) ? 1 : 0;
+                }
+                s_ts[r] = ts; s_code[r] = cd;
+            }
+            __syncthreads();
+            // ---- duplicates (adjacent), stale entries, ball conflicts with an earlier entry ----
+            for (int i = tid; i < nE; i += T) {
+                const uint64_t ts = s_ts[i], cd = s_code[i];
+                int f = 0;
+                if (cd == BL_CODE_STALE) f = F_STALE;
+                else if (i > 0 && s_ts[i - 1] == ts && s_code[i - 1] == cd) f = F_DUP;
+                else {
+                    int a, b;
+                    key_balls(cd, a, b);
+                    for (int j = 0; j < i; j++) {
+                        const uint64_t c2 = s_code[j];
+                        if (c2 == cd) continue;
+                        int a2, b2;
+                        key_balls(c2, a2, b2);
+                        if (a2 >= 0 && (a2 == a || a2 == b || (b2 >= 0 && (b2 == a || b2 == b)))) { f = F_CONFLICT; break; }
+                    }
+                }
+                s_flag[i] = f;
+                if (f & (F_STALE | F_CONFLICT)) atomicMin(&misc[M_CUT], i);
+            }
+            __syncthreads();
+            const int cut = misc[M_CUT] < nE ? misc[M_CUT] : nE;
+            const uint64_t ts0 = s_ts[0];
+            if (final_stage == 0 && max_reached) {
+                stop_kind = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
+            } else if (cut == 0) {
+                repair = true;  // the front entry is only a lower bound (it cannot be a conflict)
+            } else if (final_stage != 0) {
+                stop_kind = BL_STOP_TIME;  // query rounds only look at the front entry
+            } else if (ts0 == BL_TS_NAN) {
+                stop_kind = BL_STOP_ERROR; st_status = BL_ENAN;
+            } else if (ts0 >= end_excl) {
+                stop_kind = BL_STOP_TIME;
+            } else if (want_log && done >= P.log.cap) {
+                stop_kind = BL_STOP_LOG;
+            } else {
+                long long allowed = mode == MODE_ARGMIN ? 1 : m_max;
+                if (P.max_events >= 0 && P.max_events - done < allowed) allowed = P.max_events - done;
+                if (want_log && P.log.cap - done < allowed) allowed = P.log.cap - done;
+                // entries below the cut, duplicates skipped, in order
+                int r = 0;
+                for (int i = 0; i < cut && r < allowed; i++)
+                    if (!(s_flag[i] & F_DUP) && s_ts[i] < end_excl) r++;
+                nf = r;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) misc[M_CUT] = BL_EV_CAP;
+        if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
+
+        // =========================== repair: re-read the rows of all stale candidates ========================
+        if (repair) {
+            if (own && mcode == BL_CODE_STALE) dirty[atomicAdd(&misc[M_NDIRTY], 1)] = tid;
+            __syncthreads();
+            const int nd = misc[M_NDIRTY];
+            for (int d = warp; d < nd; d += nwarps) {
+                const int dt = dirty[d], dk = base + dt;
+                rescan_row(S.toi + (size_t)dk * (size_t)S.pitch, n, dk, lane, scratch + 2 * dt);
+            }
+            __syncthreads();
+            if (own && mcode == BL_CODE_STALE) { mts = scratch[2 * tid]; mcode = scratch[2 * tid + 1]; }
+            if (tid == 0) misc[M_NDIRTY] = 0;
+            if (prof_thread) { prof[3] += clock64() - c0; prof[4]++; n_rescans += nd; }
+            __syncthreads();
+            continue;
+        }
+
+        // =========================== stop / query stages ====================================================
+        if (stop_kind >= 0) {
+            const bool writer = cta == 0 && tid == 0;
+            const uint64_t cd = nE > 0 ? s_code[0] : BL_CODE_END;
+            const double t = nE > 0 ? bl_unsortable(s_ts[0]) : BL_INF;
             if (final_stage == 0) {
-                stop = bc.stop; status = bc.status;
-                if (status != BL_OK) { err_i = bc.a; err_j = bc.b; now = bc.t; }  // the reference has moved to t
-                if (stop == BL_STOP_TIME && P.end_time < BL_INF) now = P.end_time;  // _move(end_time), simulation.py:436
-                final_stage = 1; mode = MODE_BB;
+                if (writer) {
+                    double tnow = now;
+                    res->err_i = -1; res->err_j = -1;
+                    if (st_status != BL_OK) { int a, b; key_balls(cd, a, b); res->err_i = a; res->err_j = b; tnow = t; }
+                    if (stop_kind == BL_STOP_TIME && P.end_time < BL_INF) tnow = P.end_time;  // _move(end_time), :436
+                    res->time = tnow; res->stop = stop_kind; res->status = st_status;
+                    res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb;
+                    res->n_logged = want_log ? done : 0;
+                }
+                final_stage = 1; kindmask = KIND_BB; mode = MODE_ARGMIN;
+                __syncthreads();
                 continue;
             }
             if (final_stage == 1) {
-                const uint64_t cd = bc.code;
-                if (cd != BL_CODE_NONE && cd != BL_CODE_END && bc.t < BL_INF) {
-                    bb_t = bc.t; bb_i = bl_code_lo(cd); bb_j = bl_code_hi(cd);
+                if (writer) {
+                    if (P.query_only) { res->time = P.time; res->err_i = -1; res->err_j = -1; }
+                    const bool some = cd != BL_CODE_NONE && cd != BL_CODE_END && t < BL_INF;
+                    res->bb_t = some ? t : BL_INF; res->bb_i = some ? bl_code_lo(cd) : -1; res->bb_j = some ? bl_code_hi(cd) : 0;
                 }
-                final_stage = 2; mode = MODE_BO;
+                final_stage = 2; kindmask = KIND_BO;
+                __syncthreads();
                 continue;
             }
-            {
-                const uint64_t cd = bc.code;
-                if (cd != BL_CODE_END) {
-                    // numpy argmin over _obstacles_toi: first ball attaining the minimum, even when it is +inf
-                    bo_t = bc.t; bo_ball = (long long)(cd & ~BL_CODE_OBS); bo_obs = bc.obs; bo_arg = bc.q_arg;
-                }
+            if (writer) {
+                // numpy argmin over _obstacles_toi: first ball attaining the minimum, even when it is +inf
+                const bool some = cd != BL_CODE_END;
+                const long long ball = some ? (long long)(cd & ~BL_CODE_OBS) : -1;
+                res->bo_t = some ? t : BL_INF; res->bo_ball = ball;
+                res->bo_obs = some ? (long long)__ldcg(S.obs_idx + ball) : -1;
+                res->bo_arg = some ? __ldcg(S.obs_arg + ball) : 0.0;
             }
             break;
         }
 
-        // ---- apply the event: every owner re-solves its pair(s) with the colliding ball(s) ---------------
-        const double t = bc.t;
-        const int a = bc.a, b = bc.b;  // b == -1 for an obstacle event
-        const double ax = bc.ax, ay = bc.ay, avx = bc.avx, avy = bc.avy;
-        const double bx = bc.bx, by = bc.by, bvx = bc.bvx, bvy = bc.bvy;
-        const int rca = bc.rca, rcb = bc.rcb;
-        for (int u = 0; u < bpt; u++) {
-            const int kl = u * nthreads + tid, k = kbase + kl;
-            if (k >= n) continue;
-            if (k == a || k == b) {
-                const bool is_a = (k == a);
-                const double px = is_a ? ax : bx, py = is_a ? ay : by, wx = is_a ? avx : bvx, wy = is_a ? avy : bvy;
-                M.d(F_P0X, kl) = px; M.d(F_P0Y, kl) = py; M.d(F_VX, kl) = wx; M.d(F_VY, kl) = wy; M.d(F_T0, kl) = t;
-                M.d(F_MT, kl) = BL_INF; M.mcode[kl] = BL_CODE_NONE;
-                // keep the global mirror current: stale-row repairs read partner states from it
-                __stcg(S.p0x + k, px); __stcg(S.p0y + k, py); __stcg(S.vx + k, wx); __stcg(S.vy + k, wy);
-                __stcg(S.t0 + k, t);
-                if (is_a && b >= 0) {  // toi_table[idx2][idx1] = INF, simulation.py:458
-                    __stcg(S.toi + (size_t)a * pitch + b, BL_INF);
-                    __stcg(S.toi + (size_t)b * pitch + a, BL_INF);
+        // =========================== 3. resolve: one thread per collision of the batch ========================
+        // rank = position among the non-duplicate entries; the batch is the first nf of them
+        for (int i = tid; i < nE; i += T) {
+            if (s_flag[i] & F_DUP) continue;
+            int r = 0;
+            for (int j = 0; j < i; j++) r += (s_flag[j] & F_DUP) ? 0 : 1;
+            if (r >= nf) continue;
+            const uint64_t ts = s_ts[i], cd = s_code[i];
+            const double t = bl_unsortable(ts);
+            double *pl = r_pay + 13 * r;
+            int st = BL_OK;
+            if (cd & BL_CODE_OBS) {
+                // ---- ball-obstacle, simulation.py:504-519 + :604-636 ----
+                const int a = (int)(cd & 0x7fffffffull);
+                const double q0x = __ldcg(S.p0x + a), q0y = __ldcg(S.p0y + a), wvx = __ldcg(S.vx + a), wvy = __ldcg(S.vy + a);
+                const double wt0 = __ldcg(S.t0 + a), qarg = __ldcg(S.obs_arg + a);
+                const int oi = __ldcg(S.obs_idx + a);
+                const double ax = bl_advance(q0x, wvx, t, wt0), ay = bl_advance(q0y, wvy, t, wt0);
+                double nvx = wvx, nvy = wvy;
+                st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, wvx, wvy, qarg, nvx, nvy) : BL_EASSERT;
+                bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t;
+                bid[2 * r] = a; brc[2 * r] = S.rclass[a];
+                bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
+                pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
+                pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
+                r_info[4 * r] = st; r_info[4 * r + 1] = oi; r_info[4 * r + 2] = 0;
+                if (a >= base && a < base + T) brank[a - base] = r;
+            } else {
+                // ---- ball-ball, simulation.py:446-455 + :562-602 (a = idx1 < b = idx2) ----
+                const int a = bl_code_lo(cd), b = bl_code_hi(cd);
+                const double a0x = __ldcg(S.p0x + a), a0y = __ldcg(S.p0y + a), a_vx = __ldcg(S.vx + a), a_vy = __ldcg(S.vy + a);
+                const double a_t0 = __ldcg(S.t0 + a);
+                const double b0x = __ldcg(S.p0x + b), b0y = __ldcg(S.p0y + b), b_vx = __ldcg(S.vx + b), b_vy = __ldcg(S.vy + b);
+                const double b_t0 = __ldcg(S.t0 + b);
+                double m1 = S.mass[a], m2 = S.mass[b];
+                const double ax = bl_advance(a0x, a_vx, t, a_t0), ay = bl_advance(a0y, a_vy, t, a_t0);
+                const double bxx = bl_advance(b0x, b_vx, t, b_t0), byy = bl_advance(b0y, b_vy, t, b_t0);
+                bl_remap_masses(m1, m2);
+                double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
+                st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
+                bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t;
+                bid[2 * r] = a; brc[2 * r] = S.rclass[a];
+                bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
+                bid[2 * r + 1] = b; brc[2 * r + 1] = S.rclass[b];
+                pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
+                pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
+                r_info[4 * r] = st; r_info[4 * r + 1] = -1; r_info[4 * r + 2] = 1;
+                if (a >= base && a < base + T) brank[a - base] = r;
+                if (b >= base && b < base + T) brank[b - base] = r;
+            }
+            if (st != BL_OK) atomicMin(&misc[M_ERRRANK], r);
+        }
+        __syncthreads();
+        const int er = misc[M_ERRRANK];
+        __syncthreads();
+        if (er < nf) {
+            // the collision at this rank cannot be resolved (physics.py:277-279 / zero masses): commit what comes
+            // before it; if it is the front one, stop here with the reference's error
+            if (tid == 0) misc[M_ERRRANK] = BL_EV_CAP;
+            if (er == 0) {
+                if (cta == 0 && tid == 0) {
+                    res->err_i = bid[0]; res->err_j = bid[1];
+                    res->time = bt[0];  // the reference has moved to t
+                    res->stop = BL_STOP_ERROR; res->status = r_info[0];
+                    res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb;
+                    res->n_logged = want_log ? done : 0;
                 }
-                double ot, oarg; int oi;
-                bl_next_obstacle<FMA>(M.obs, n_obs, S.rsum2_obs, K, M.i(I_RC, kl), px, py, wx, wy, M.d(F_RADIUS, kl), t,
-                                      ot, oi, oarg);
-                M.d(F_OT, kl) = ot; M.i(I_OIDX, kl) = oi; M.d(F_OARG, kl) = oarg;
+                now = bt[0];
+                final_stage = 1; kindmask = KIND_BB; mode = MODE_ARGMIN;
+                __syncthreads();
+                brank[tid] = -1;
+                __syncthreads();
                 continue;
             }
-            const double vx = M.d(F_VX, kl), vy = M.d(F_VY, kl), t0 = M.d(F_T0, kl);
-            const double px = bl_advance(M.d(F_P0X, kl), vx, t, t0), py = bl_advance(M.d(F_P0Y, kl), vy, t, t0);
-            const int rck = M.i(I_RC, kl);
-            const double na = bl_add(t, bl_toi_ball_ball<FMA>(ax, ay, avx, avy, px, py, vx, vy,
-                                                              __ldg(S.rsum2 + (size_t)rca * K + rck)));
-            __stcg(S.toi + (size_t)a * pitch + k, na);
-            __stcg(S.toi + (size_t)k * pitch + a, na);
-            uint64_t c_ts = bl_sortable(na), c_code = na < BL_INF ? bl_pair_code(k, a) : BL_CODE_NONE;
-            bool c_is_a = true;
-            if (b >= 0) {
-                const double nb = bl_add(t, bl_toi_ball_ball<FMA>(bx, by, bvx, bvy, px, py, vx, vy,
-                                                                  __ldg(S.rsum2 + (size_t)rcb * K + rck)));
-                __stcg(S.toi + (size_t)b * pitch + k, nb);
-                __stcg(S.toi + (size_t)k * pitch + b, nb);
-                const uint64_t b_ts = bl_sortable(nb), b_code = nb < BL_INF ? bl_pair_code(k, b) : BL_CODE_NONE;
-                if (bl_key_less(b_ts, b_code, c_ts, c_code)) { c_ts = b_ts; c_code = b_code; c_is_a = false; }
+            nf = er;
+        }
+        if (prof_thread) { const long long c2 = clock64(); prof[1] += c2 - c0; c0 = c2; }
+
+        // =========================== 4. solve: my pair with every ball of the batch ===========================
+        int myrank = brank[tid];
+        if (myrank >= nf) myrank = -1;
+        const uint64_t vbound = bl_sortable(bt[2 * (nf - 1)]);  // time of the last collision of the batch
+        uint64_t vmin = ~0ull;
+        double nx = 0, ny = 0, nvx = 0, nvy = 0, nt0 = 0;   // my state after my own collision (batch balls only)
+        uint64_t n_ots = 0;
+        if (own) {
+            if (myrank >= 0) {
+                const int myj = bid[2 * myrank] == k ? 2 * myrank : 2 * myrank + 1;
+                nx = bx[myj]; ny = by[myj]; nvx = bvx[myj]; nvy = bvy[myj]; nt0 = bt[myj];
+                // my next obstacle after the collision, simulation.py:490-495 / :545-547
+                double ot, oarg;
+                int oi;
+                bl_next_obstacle<FMA>(obs, n_obs, S.rsum2_obs, K, myrc, nx, ny, nvx, nvy, c_radius[tid], nt0, ot, oi, oarg);
+                n_ots = bl_sortable(ot);
+                scratch[2 * tid] = as_u(oarg); scratch[2 * tid + 1] = (uint64_t)(unsigned)oi;
+                if (n_ots <= vbound && myrank < nf - 1) vmin = n_ots;
             }
-            // fold the new value(s) into the candidate of ball k
-            const uint64_t o_code = M.mcode[kl], o_ts = bl_sortable(M.d(F_MT, kl));
-            bool take = false;
-            if (o_code != BL_CODE_STALE && o_code != BL_CODE_NONE) {
-                const int q = bl_code_hi(o_code) == k ? bl_code_lo(o_code) : bl_code_hi(o_code);
-                if (q == a || q == b) {
-                    // the entry that was the candidate has just been overwritten
-                    if (!bl_key_less(o_ts, o_code, c_ts, c_code)) take = true;  // new <= old: still the minimum
-                    else M.mcode[kl] = BL_CODE_STALE;                               // old time stays as a lower bound
-                } else {
-                    take = bl_key_less(c_ts, c_code, o_ts, o_code);
-                }
-            } else {
-                take = bl_key_less(c_ts, c_code, o_ts, o_code);  // stale: only a strictly earlier time is decisive
-            }
-            if (take && c_code != BL_CODE_NONE) {
-                M.d(F_MT, kl) = bl_unsortable(c_ts); M.mcode[kl] = c_code;
-                M.d(F_QP0X, kl) = c_is_a ? ax : bx; M.d(F_QP0Y, kl) = c_is_a ? ay : by;
-                M.d(F_QVX, kl) = c_is_a ? avx : bvx; M.d(F_QVY, kl) = c_is_a ? avy : bvy;
-                M.d(F_QT0, kl) = t; M.d(F_QMASS, kl) = c_is_a ? bc.amass : bc.bmass;
-                M.i(I_QRC, kl) = c_is_a ? rca : rcb;
+            const int nb = 2 * nf;
+            for (int j = 0; j < nb; j++) {
+                const int x = bid[j];
+                const int r = j >> 1;
+                if (x < 0 || r == myrank) continue;  // no ball, me, or my partner in the same collision
+                const double t = bt[j];
+                // my state as of just before that collision
+                const bool after = myrank >= 0 && myrank < r;
+                const double sx = after ? nx : p0x, sy = after ? ny : p0y, svx = after ? nvx : vx, svy = after ? nvy : vy;
+                const double st0 = after ? nt0 : t0;
+                const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
+                const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
+                const double v = bl_add(t, bl_toi_ball_ball<FMA>(bx[j], by[j], bvx[j], bvy[j], px, py, svx, svy, rs));
+                stash[(size_t)j * T + tid] = v;
+                const uint64_t vs = bl_sortable(v);
+                if (vs <= vbound && r < nf - 1) vmin = vs < vmin ? vs : vmin;
             }
         }
-        now = t;
-        if (kind == EV_BB) n_bb++; else n_bo++;
-        if (P.log.cap > 0) n_logged++;
-        mode = MODE_BOTH;
-        prof[2] += clock64() - c2;
-        // no barrier needed here: the next writer of `bc` is warp 0 after the next __syncthreads pair
+        if (nf > 1) {
+            const uint64_t wmin = warp_min_u64(vmin);
+            if (lane == 0 && wmin != ~0ull) atomicMin(m_viol, (unsigned long long)wmin);
+            __syncthreads();
+            if (ncta > 1) {
+                if (tid == 0) __stcg(P.viol + (size_t)par * BL_MAX_CTAS + cta, (uint64_t)*m_viol);
+                sync_all(P, epoch);
+                uint64_t h = ~0ull;
+                for (int c = lane; c < ncta; c += 32) {
+                    const uint64_t v2 = __ldcg(P.viol + (size_t)par * BL_MAX_CTAS + c);
+                    h = v2 < h ? v2 : h;
+                }
+                vmin = warp_min_u64(h);
+            } else {
+                vmin = (uint64_t)*m_viol;
+            }
+            __syncthreads();
+            if (tid == 0) *m_viol = ~0ull;
+        } else {
+            vmin = ~0ull;
+        }
+        // collisions committed: the first one always, the others while they come before every violation
+        int nc = 1;
+        while (nc < nf && bl_sortable(bt[2 * nc]) < vmin) nc++;
+        if (prof_thread) { const long long c3 = clock64(); prof[2] += c3 - c0; c0 = c3; }
+
+        // =========================== 5. commit ===============================================================
+        if (own) {
+            const bool mine = myrank >= 0 && myrank < nc;  // my own collision is committed
+            // the new values I am responsible for, folded into one candidate
+            uint64_t c_ts = ts_inf, c_code = BL_CODE_NONE;
+            bool partner_hit = false;
+            int q = -1;
+            if (!mine && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
+            const int nb = 2 * nc;
+            for (int j = 0; j < nb; j++) {
+                const int x = bid[j];
+                const int r = j >> 1;
+                if (x < 0) continue;
+                if (r == myrank) {
+                    // toi_table[idx2][idx1] = INF, simulation.py:458 (the lower index stores both cells)
+                    if (x != k && k < x) {
+                        __stcg(myrow + x, BL_INF);
+                        __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
+                    }
+                    continue;
+                }
+                if (mine && r < myrank) continue;  // that pair is re-solved at my (later) collision by x's owner
+                const double v = stash[(size_t)j * T + tid];
+                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
+                __stcg(myrow + x, v);
+                if (x == q) partner_hit = true;
+                if (v < BL_INF) {
+                    const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
+                    if (bl_key_less(vs, vc, c_ts, c_code)) { c_ts = vs; c_code = vc; }
+                }
+            }
+            if (mine) {
+                // my cover is emptied and refilled with the pairs solved at later collisions of the batch
+                mts = c_code != BL_CODE_NONE ? c_ts : ts_inf; mcode = c_code;
+                p0x = nx; p0y = ny; vx = nvx; vy = nvy; t0 = nt0;
+                ots = n_ots;
+                c_oarg[tid] = as_d(scratch[2 * tid]);
+                c_oidx[tid] = (int)scratch[2 * tid + 1];
+                // keep the global mirror current: resolvers read ball states from it
+                __stcg(S.p0x + k, p0x); __stcg(S.p0y + k, p0y); __stcg(S.vx + k, vx); __stcg(S.vy + k, vy);
+                __stcg(S.t0 + k, t0);
+                __stcg(S.obs_arg + k, c_oarg[tid]); __stcg(S.obs_idx + k, c_oidx[tid]);
+            } else if (mcode == BL_CODE_STALE) {
+                if (c_code != BL_CODE_NONE && c_ts < mts) { mts = c_ts; mcode = c_code; }  // strictly earlier: decisive
+            } else if (partner_hit) {
+                // the entry that was my candidate has just been overwritten
+                if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { mts = c_ts; mcode = c_code; }
+                else mcode = BL_CODE_STALE;  // the old time stays as a lower bound
+            } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
+                mts = c_ts; mcode = c_code;
+            }
+        }
+        // event log, simulation.py:590-594 / :626-631 payloads
+        if (want_log && cta == 0) {
+            for (int r = tid; r < nc; r += T) {
+                const long long e = done + r;
+                const double *pl = r_pay + 13 * r;
+                const bool bb = r_info[4 * r + 2] != 0;
+                P.log.t[e] = pl[12]; P.log.i[e] = bid[2 * r];
+                P.log.j[e] = bb ? (long long)bid[2 * r + 1] : -1 - (long long)r_info[4 * r + 1];
+                if (P.log.payload) {
+                    double *o = P.log.payload + 12 * e;
+#pragma unroll
+                    for (int f = 0; f < 12; f++) o[f] = pl[f];
+                }
+            }
+        }
+        for (int r = 0; r < nc; r++) n_bb += r_info[4 * r + 2];
+        done += nc;
+        prev_now = now;
+        now = bt[2 * (nc - 1)];
+        // ---- next window ----
+        if (mode == MODE_ARGMIN) {
+            kindmask = KIND_BOTH;  // only the first event's kind was forced
+            if (!(win > 0.0)) {
+                const double gap = bl_sub(now, prev_now);
+                if (done >= 2 && gap > 0.0) win = bl_mul(gap, (double)P.target);
+            }
+            if (win > 0.0) mode = MODE_WINDOW;
+        } else {
+            if (nc < nf) win = bl_mul(win, 0.5);
+            else if (2 * nE < P.target) win = bl_mul(win, 1.5);
+            else if (nE > P.target + (P.target >> 1)) win = bl_mul(win, 0.75);
+        }
+        __syncthreads();
+        brank[tid] = -1;
+        if (prof_thread) prof[6] += clock64() - c0;
+        // the next barrier (post) orders this round's global stores before anybody reads them
     }
 
     // ---- write back the resident cache ------------------------------------------------------------------
-    for (int u = 0; u < bpt; u++) {
-        const int kl = u * nthreads + tid, k = kbase + kl;
-        if (k < n) {
-            S.cover_t[k] = M.d(F_MT, kl); S.cover_code[k] = M.mcode[kl];
-            S.obs_t[k] = M.d(F_OT, kl); S.obs_idx[k] = M.i(I_OIDX, kl); S.obs_arg[k] = M.d(F_OARG, kl);
-        }
+    if (own) {
+        S.cover_t[k] = bl_unsortable(mts); S.cover_code[k] = mcode;
+        S.obs_t[k] = bl_unsortable(ots);
+        S.obs_idx[k] = c_oidx[tid];
+        S.obs_arg[k] = c_oarg[tid];
     }
-    if (tid == 0 && n_rescans) atomicAdd((unsigned long long *)&P.result->n_rescans, (unsigned long long)n_rescans);
-    if (rank == 0 && tid == 0) {
-        bl_result *r = P.result;
-        r->time = now; r->n_ball_ball = n_bb; r->n_ball_obstacle = n_bo;
-        r->bb_t = bb_t; r->bb_i = bb_i; r->bb_j = bb_j;
-        r->bo_t = bo_t; r->bo_ball = bo_ball; r->bo_obs = bo_obs; r->bo_arg = bo_arg;
-        r->status = status; r->stop = stop; r->n_logged = n_logged; r->err_i = err_i; r->err_j = err_j;
-        for (int q = 0; q < 8; q++) r->prof[q] = prof[q];
+    if (tid == 0 && n_rescans) atomicAdd((unsigned long long *)&res->n_rescans, (unsigned long long)n_rescans);
+    if (cta == 0 && tid == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) res->prof[q] = prof[q];
+        res->window = win;
     }
-    cluster_sync_all();  // nobody exits while a peer may still post into its inbox
+    if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-int bl_evolve_pick_config(const bl_handle *h, int n, int *cluster, int *threads, int *bpt) {
-    if (n <= 0) { *cluster = 1; *threads = 32; *bpt = 1; return BL_OK; }
-    int c = 1, t = ((n + 31) / 32) * 32, b = 1;
-    if (t > BL_MAX_THREADS) {
-        t = BL_MAX_THREADS;
-        c = (n + BL_MAX_THREADS - 1) / BL_MAX_THREADS;
+// CTA shape: one ball per thread.  Up to 2048 balls run as one cluster of <= 16 small CTAs (hardware barrier);
+// larger systems use one CTA of >= 128 threads per SM and a cooperative launch.
+int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode) {
+    if (n <= 0) { *ncta = 1; *threads = 32; *sync_mode = SYNC_CTA; return BL_OK; }
+    if (n <= 64) { *ncta = 1; *threads = ((n + 31) / 32) * 32; *sync_mode = SYNC_CTA; return BL_OK; }
+    if (n <= 2048) {
+        int c = (n + 127) / 128;
+        if (c < 2) c = 2;
         int p = 1;
-        while (p < c) p <<= 1;
+        while (p < c) p <<= 1;  // cluster sizes: powers of two
         c = p;
-        if (c > h->max_cluster) {
-            c = h->max_cluster;
-            b = (n + c * t - 1) / (c * t);
-        }
+        int t = (n + c - 1) / c;
+        t = ((t + 31) / 32) * 32;
+        *ncta = c; *threads = t; *sync_mode = SYNC_CLUSTER;
+        return BL_OK;
     }
-    *cluster = c; *threads = t; *bpt = b;
-    size_t need = smem_bytes(t * b, 8);
-    if (need > h->max_smem_optin) return BL_EUNSUPPORTED;
+    int t = 128;
+    const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    while ((n + t - 1) / t > sms && t <= BL_MAX_THREADS) t += 32;
+    if (t > BL_MAX_THREADS) return BL_EUNSUPPORTED;
+    *ncta = (n + t - 1) / t; *threads = t; *sync_mode = SYNC_GRID;
     return BL_OK;
 }
 
-template <bool FMA>
-static int launch_t(bl_handle *h, const Params &P, int cluster, int threads, size_t smem, cudaStream_t st) {
-    auto kern = bl_evolve_kernel<FMA>;
+static int pick_m_max(int threads) {
+    int m = (BL_STASH_BYTES / 16) / threads;  // 2 values of 8 bytes per collision and thread
+    if (m > BL_M_MAX) m = BL_M_MAX;
+    if (m < 1) m = 1;
+    return m;
+}
+
+template <bool FMA, int MAXT>
+static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
+    auto kern = bl_evolve_kernel<FMA, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaFuncSetAttribute(smem)");
-    if (cluster > 8) {
+    if (P.sync_mode == SYNC_GRID) {
+        void *args[1] = {(void *)&P};
+        e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)P.ncta), dim3((unsigned)P.T), args, smem, st);
+        return bl_check_cuda(h, e, "cooperative launch of bl_evolve_kernel");
+    }
+    if (P.ncta > 8) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaFuncSetAttribute(non-portable cluster)");
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)cluster, 1, 1);
-    cfg.blockDim = dim3((unsigned)threads, 1, 1);
+    cfg.gridDim = dim3((unsigned)P.ncta, 1, 1);
+    cfg.blockDim = dim3((unsigned)P.T, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.x = (unsigned)P.ncta;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -583,25 +804,39 @@ static int launch_t(bl_handle *h, const Params &P, int cluster, int threads, siz
 
 int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st) {
-    int cluster, threads, bpt;
-    int rc = bl_evolve_pick_config(h, s->n, &cluster, &threads, &bpt);
+    int ncta, threads, sync_mode;
+    int rc = bl_evolve_pick_config(h, s->n, &ncta, &threads, &sync_mode);
     if (rc != BL_OK)
-        return bl_set_error(h, rc, "event kernel keeps ball state resident in shared memory: n=%d does not fit "
-                            "%d CTAs x %d threads", s->n, cluster, threads);
+        return bl_set_error(h, rc, "the event kernel keeps ball state resident on chip: n=%d exceeds %d CTAs x %d "
+                            "threads", s->n, h->sm_count, BL_MAX_THREADS);
     Params P;
     P.s = *s;
     P.time = time; P.end_time = end_time; P.max_events = max_events; P.first_kind = first_kind;
     P.query_only = query_only;
     if (log) P.log = *log; else { P.log.cap = 0; P.log.t = nullptr; P.log.i = nullptr; P.log.j = nullptr; P.log.payload = nullptr; }
     P.result = h->d_result;
-    P.cap = threads * bpt;
-    P.bpt = bpt;
-    size_t smem = smem_bytes(P.cap, s->n_obstacles);
+    P.T = threads; P.ncta = ncta; P.sync_mode = sync_mode;
+    P.m_max = pick_m_max(threads);
+    // collisions per round the window aims at: the chance that a round is cut short grows like 2 m^2 / n
+    int target = 1;
+    while ((long long)(target + 1) * (target + 1) * 20 <= (long long)s->n) target++;
+    if (target > (2 * P.m_max) / 3) target = (2 * P.m_max) / 3;
+    if (target < 1) target = 1;
+    if (h->target_override > 0) target = h->target_override < P.m_max ? h->target_override : P.m_max;
+    P.target = target;
+    // the window length found by the previous launch on this system is a good first guess
+    P.window = (h->window_n == s->n && h->window_sys == (const void *)s->toi) ? h->window : 0.0;
+    P.bar = h->d_bar; P.post = h->d_post; P.viol = h->d_viol;
+    size_t smem = (size_t)make_layout(P.T, P.m_max, s->n_obstacles).words * 8;
     if (smem > h->max_smem_optin)
         return bl_set_error(h, BL_EUNSUPPORTED, "event kernel needs %zu B of shared memory per CTA (limit %zu)", smem,
                             h->max_smem_optin);
     cudaError_t e = cudaMemsetAsync(h->d_result, 0, sizeof(bl_result), st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset result");
+    e = cudaMemsetAsync(h->d_bar, 0, 64, st);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "memset barrier");
     h->launches++;
-    return h->dot_fma ? launch_t<true>(h, P, cluster, threads, smem, st) : launch_t<false>(h, P, cluster, threads, smem, st);
+    if (threads <= 256)
+        return h->dot_fma ? launch_t<true, 256>(h, P, smem, st) : launch_t<false, 256>(h, P, smem, st);
+    return h->dot_fma ? launch_t<true, BL_MAX_THREADS>(h, P, smem, st) : launch_t<false, BL_MAX_THREADS>(h, P, smem, st);
 }

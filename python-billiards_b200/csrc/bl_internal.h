@@ -15,11 +15,25 @@ struct bl_handle {
     cudaEvent_t ev0, ev1;
     float last_ms;
     long long launches;
+    // event kernel exchange buffers (global memory; see bl_evolve.cu)
+    unsigned *d_bar;          // grid barrier counter
+    uint64_t *d_post;         // [2][BL_MAX_CTAS][BL_POST_WORDS] keys posted by each CTA
+    uint64_t *d_viol;         // [2][BL_MAX_CTAS] earliest violating new key of each CTA
+    // window length the last launch ended with, and the system it belongs to
+    double window;
+    int window_n;
+    const void *window_sys;
+    int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
     char err[512];
 };
 
 #define BL_MAX_THREADS 1024
-#define BL_EVOLVE_BYTES_PER_BALL 160  // shared memory per resident ball in the event kernel (see bl_evolve.cu)
+#define BL_MAX_CTAS 160       // >= SM count
+#define BL_POST_WORDS 16      // header + BL_R_POST keys of 2 words
+#define BL_R_POST 6           // keys one CTA may post per round
+#define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
+#define BL_M_MAX 48           // collisions committed per round, at most
+#define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
 
 int bl_set_error(bl_handle *h, int code, const char *fmt, ...);
 int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what);
@@ -27,7 +41,7 @@ int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what);
 // bl_evolve.cu
 int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st);
-int bl_evolve_pick_config(const bl_handle *h, int n, int *cluster, int *threads, int *bpt);
+int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode);
 // bl_table.cu
 int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st);
 int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st);

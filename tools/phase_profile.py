@@ -17,7 +17,7 @@ from billiards import _lib  # noqa: E402
 
 fma = _lib.probe_dot_fma()
 h = _lib.get_handle(0, fma)
-NAMES = ("argmin+barrier", "resolve", "solve+update", "repair")
+NAMES = ("post+collect+sort", "resolve", "solve+violation", "repair")
 
 
 def run(cfg, events, label):
@@ -33,9 +33,12 @@ def run(cfg, events, label):
     n = sum(c)
     ms = h.last_kernel_ms()
     prof = [int(x) for x in r.prof]
-    per = {k: prof[q] / max(n, 1) for q, k in enumerate(NAMES)}
+    rounds = max(prof[5], 1)
+    per = {k: round(prof[q] / rounds) for q, k in enumerate(NAMES)}
+    per["commit"] = round(prof[6] / rounds)
     print(f"{label}: N={cfg.n} events={n} kernel={ms:.2f} ms -> {n / ms * 1e3:,.0f} coll/s ({ms * 1e3 / max(n,1):.2f} us/event); "
-          f"cycles/event {per}; repair phases {prof[4]} rows {int(r.n_rescans)} iterations {prof[5]}", flush=True)
+          f"rounds {prof[5]} ({n / rounds:.1f} events/round, {prof[7]} re-posted); cycles/round {per}; "
+          f"repair phases {prof[4]} rows {int(r.n_rescans)}; window {r.window:.3g}", flush=True)
 
 
 if __name__ == "__main__":
@@ -47,7 +50,7 @@ if __name__ == "__main__":
     c = b.evolve(16)
     dt = time.perf_counter() - t0
     print(f"galperin: {c} in {dt * 1e3:.1f} ms wall, kernel {h.last_kernel_ms():.1f} ms -> {sum(c) / dt:,.0f} coll/s; "
-          f"cycles/event {[int(x) / sum(c) for x in b.last_result.prof[:4]]}", flush=True)
+          f"rounds {b.last_result.prof[5]} cycles/round {[int(x) // max(b.last_result.prof[5], 1) for x in b.last_result.prof[:4]]}", flush=True)
     p = workloads.pool().build(billiards, dot_fma=fma)
     t0 = time.perf_counter()
     c = p.evolve(100)
