@@ -34,7 +34,8 @@ class BlSystem(ctypes.Structure):
                 ("n_obstacles", ctypes.c_int32),
                 ("p0x", c_void), ("p0y", c_void), ("vx", c_void), ("vy", c_void), ("t0", c_void),
                 ("radius", c_void), ("mass", c_void), ("rclass", c_void), ("rsum2", c_void), ("rsum2_obs", c_void),
-                ("obstacles", c_void), ("toi", c_void), ("cover_t", c_void), ("cover_code", c_void),
+                ("obstacles", c_void), ("toi", c_void), ("seq", c_void), ("seq_counter", c_void),
+                ("cover_t", c_void), ("cover_code", c_void),
                 ("obs_t", c_void), ("obs_idx", c_void), ("obs_arg", c_void)]
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "bl_apply_edits": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void, c_void]),
     "bl_host_pow2_table": (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, c_double_p]),
     "bl_rebuild_cover": (ctypes.c_int, [_H, _SYS, c_void]),
+    "bl_symmetrize": (ctypes.c_int, [_H, _SYS, c_void]),
     "bl_row_minima": (ctypes.c_int, [_H, _SYS, c_void, c_void, c_void]),
     "bl_evolve": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int,
                                  ctypes.POINTER(BlLog), ctypes.POINTER(BlResult), c_void]),

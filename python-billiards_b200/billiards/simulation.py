@@ -73,6 +73,7 @@ class Billiard:
         self._classes = {}     # radius -> class index
         self._class_radii = []
 
+        self._table_dirty = False  # table rows written by the event kernel, mirrors not yet refreshed
         self._next = None      # cached BlResult with the next collisions
         self.last_result = None
 
@@ -99,10 +100,17 @@ class Billiard:
         new["rclass"] = torch.zeros(cap, dtype=torch.int32, device=dev)
         new["obs_idx"] = torch.full((cap,), -1, dtype=torch.int32, device=dev)
         new["cover_code"] = torch.zeros(cap, dtype=torch.int64, device=dev)
+        new["seq"] = torch.zeros(cap, dtype=torch.int64, device=dev)
+        new["seq_counter"] = self._dev.get("seq_counter", None)
+        if new["seq_counter"] is None:
+            new["seq_counter"] = torch.zeros(1, dtype=torch.int64, device=dev)
         new["toi"] = torch.full((cap, pitch), INF, dtype=torch.float64, device=dev)
         n = self._n
         if n:
+            self._table_sync()
             for name in new:
+                if name == "seq_counter":
+                    continue
                 if name == "toi":
                     new["toi"][:n, :n] = self._dev["toi"][:n, :n]
                 else:
@@ -121,9 +129,18 @@ class Billiard:
         s = _lib.BlSystem()
         s.n, s.pitch, s.n_classes, s.n_obstacles = self._n, self._pitch, len(self._class_radii), len(self.obstacles)
         for name in ("p0x", "p0y", "vx", "vy", "t0", "radius", "mass", "rclass", "rsum2", "rsum2_obs", "obstacles",
-                     "toi", "cover_t", "cover_code", "obs_t", "obs_idx", "obs_arg"):
+                     "toi", "seq", "seq_counter", "cover_t", "cover_code", "obs_t", "obs_idx", "obs_arg"):
             setattr(s, name, d[name].data_ptr() if name in d else 0)
         return s
+
+    def _table_sync(self):
+        """The event kernel rewrites only the rows of colliding balls; make the mirrored cells current again
+        before anything reads whole rows of the table (bl_symmetrize)."""
+        if self._table_dirty and self._n:
+            h = self._h()
+            s = self._system()
+            h.check(h.lib.bl_symmetrize(h.h, ctypes.byref(s), h.stream()))
+        self._table_dirty = False
 
     def _upload_radii(self, first, last):
         """(Re)derive radius classes for balls [first, last) from balls_radius and refresh the pow tables."""
@@ -164,6 +181,7 @@ class Billiard:
         if not self._pending:
             return
         h = self._h()
+        self._table_sync()
         first, k = self._n, len(self._pending)
         last = first + k
         self._alloc(last)
@@ -251,12 +269,14 @@ class Billiard:
         n = self._n
         if n == 0:
             return []
+        self._table_sync()
         tab = self._dev["toi"][:n, :n].cpu().numpy()
         return [tab[i, :i].copy() for i in range(n)]
 
     def _row_minima(self):
         import torch
         self._flush()
+        self._table_sync()
         h, n = self._h(), self._n
         bt = torch.empty(max(n, 1), dtype=torch.float64, device=h.torch_device)
         bi = torch.empty(max(n, 1), dtype=torch.int64, device=h.torch_device)
@@ -371,6 +391,7 @@ class Billiard:
         else:
             idx = [int(i) for i in iter(indices)]  # TypeError if not iterable
         self._flush()
+        self._table_sync()
         h, n = self._h(), self._n
         for i in idx:
             if not -n <= i < n:
@@ -418,6 +439,8 @@ class Billiard:
         rc = h.lib.bl_evolve(h.h, ctypes.byref(s), float(self._time), float(end_time), int(max_events), int(first_kind),
                              ctypes.byref(log) if log is not None else None, ctypes.byref(res), h.stream())
         self.last_result = res
+        if res.n_ball_ball + res.n_ball_obstacle:
+            self._table_dirty = True
         if rc == _lib.BL_OK or rc in (_lib.BL_ESEPARATING, _lib.BL_EDIVZERO, _lib.BL_ENAN):
             self._time = res.time
             self._host_valid = False

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bl_internal.h"
@@ -52,6 +53,14 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
     if ((e = cudaMalloc(&h->d_post, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_POST_WORDS)) != cudaSuccess)
         return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMalloc(&h->d_viol, sizeof(uint64_t) * 2 * BL_MAX_CTAS)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
+    if ((e = cudaMalloc(&h->d_stale, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_MAX_THREADS)) != cudaSuccess)
+        return bl_check_cuda(h, e, "cudaMalloc");
+    if ((e = cudaMalloc(&h->d_partial, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_RCHUNK * 2)) != cudaSuccess)
+        return bl_check_cuda(h, e, "cudaMalloc");
+    {
+        const char *hz = getenv("BL_REPAIR_HORIZON");
+        h->repair_horizon = hz ? atof(hz) : 8.0;
+    }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     return BL_OK;
@@ -63,6 +72,8 @@ int bl_destroy(bl_handle *h) {
     if (h->d_bar) cudaFree(h->d_bar);
     if (h->d_post) cudaFree(h->d_post);
     if (h->d_viol) cudaFree(h->d_viol);
+    if (h->d_stale) cudaFree(h->d_stale);
+    if (h->d_partial) cudaFree(h->d_partial);
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -109,6 +120,12 @@ int bl_rebuild_cover(bl_handle *h, const bl_system *s, void *stream) {
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_rebuild_cover(h, s, as_stream(stream));
+}
+
+int bl_symmetrize(bl_handle *h, const bl_system *s, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    return bl_launch_symmetrize(h, s, as_stream(stream));
 }
 
 int bl_row_minima(bl_handle *h, const bl_system *s, double *d_balls_toi, int64_t *d_balls_idx, void *stream) {

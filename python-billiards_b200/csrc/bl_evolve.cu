@@ -29,8 +29,11 @@
 //
 // Data placement: a ball is owned by one thread; its state of record (p0, v, t0) and candidate keys live in
 // that thread's registers for the whole launch (mirrored to global memory when they change, so that resolvers
-// can read any ball); the symmetric table of absolute impact times stays in HBM and is only written (row of
-// the colliding ball: coalesced; column: strided) -- it is read again only to repair a stale candidate.
+// can read any ball); the table of absolute impact times stays in HBM and a collision only WRITES it: the whole
+// row of each colliding ball, coalesced.  The mirrored cells (column of the colliding ball) are left outdated --
+// a per-ball sequence number says which of toi[i][j] / toi[j][i] is current (the row of the ball whose collision
+// came later) and bl_symmetrize makes both current again before anything on the host side reads the table.  The
+// kernel reads the table only to repair stale candidates.
 // Grid: ceil(N/T) CTAs, one per SM; <= 16 CTAs run as one thread-block cluster (hardware barrier), more use a
 // cooperative launch with a global-memory barrier.
 //
@@ -71,6 +74,9 @@ struct Params {
     unsigned *bar;  // grid barrier counter (zero at launch)
     uint64_t *post; // [2][BL_MAX_CTAS][BL_POST_WORDS]
     uint64_t *viol; // [2][BL_MAX_CTAS]
+    uint64_t *stale_list; // [BL_MAX_CTAS * BL_MAX_THREADS][2] (ball, seq) of the candidates under repair
+    uint64_t *partial;    // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
+    double repair_horizon; // stale candidates within this many windows of `now` are repaired together
 };
 
 // ---- shared memory map (8-byte words) -----------------------------------------------------------------
@@ -115,7 +121,7 @@ __host__ __device__ inline Layout make_layout(int T, int m_max, int n_obs) {
     return L;
 }
 // ints of `misc`; M_VIOL is a 64-bit word index
-enum { M_PCOUNT = 0, M_ECOUNT, M_OVERFLOW, M_CUT, M_NDIRTY, M_ERRRANK };
+enum { M_PCOUNT = 0, M_ECOUNT, M_OVERFLOW, M_CUT, M_NDIRTY, M_ERRRANK, M_SBASE };
 enum { M_VIOL = 8 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -180,34 +186,6 @@ __device__ __forceinline__ void key_balls(uint64_t code, int &a, int &b) {
     else { a = bl_code_lo(code); b = bl_code_hi(code); }
 }
 
-// minimum of table row dk (all n entries, 8 loads in flight per lane) -> (ts, code) in out[0..1]
-__device__ __noinline__ void rescan_row(const double *__restrict__ row, int n, int dk, int lane, uint64_t *out) {
-    uint64_t ts = ~0ull, cd = BL_CODE_END;
-    for (int x0 = 0; x0 < n; x0 += 256) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int x = x0 + u * 32 + lane;
-            v[u] = x < n ? __ldcg(row + x) : BL_INF;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int x = x0 + u * 32 + lane;
-            if (v[u] < BL_INF && x != dk) {
-                const uint64_t s2 = bl_sortable(v[u]), c2 = bl_pair_code(dk, x);
-                if (bl_key_less(s2, c2, ts, cd)) { ts = s2; cd = c2; }
-            }
-        }
-    }
-    const int w = warp_argmin(ts, cd);
-    ts = __shfl_sync(0xffffffffu, ts, w);
-    cd = __shfl_sync(0xffffffffu, cd, w);
-    if (lane == 0) {
-        if (cd == BL_CODE_END) { out[0] = bl_sortable(BL_INF); out[1] = BL_CODE_NONE; }
-        else { out[0] = ts; out[1] = cd; }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 template <bool FMA, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constant__ Params P) {
@@ -245,7 +223,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0;
     uint64_t mts = bl_sortable(BL_INF), mcode = BL_CODE_NONE, ots = bl_sortable(BL_INF);
     int myrc = 0;
+    long long myseq = 0;  // sequence number of my last collision: toi[k][x] is current for every x with seq[x] <= myseq
+    const long long seq_base = *S.seq_counter;
     if (own) {
+        myseq = S.seq[k];
         p0x = S.p0x[k]; p0y = S.p0y[k]; vx = S.vx[k]; vy = S.vy[k]; t0 = S.t0[k];
         myrc = S.rclass[k];
         c_mass[tid] = S.mass[k];
@@ -434,18 +415,97 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         if (tid == 0) misc[M_CUT] = BL_EV_CAP;
         if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
 
-        // =========================== repair: re-read the rows of all stale candidates ========================
+        // =========================== repair: exact minima for the stale candidates near the front =============
+        // The pairs of a stale ball k that matter are those written at a LATER collision of the other ball x
+        // (seq[x] >= seq[k]); their current values sit in row x, column k.  Every owner x reads its own row at the
+        // columns of all balls under repair (its rows: a handful of pages), the minima are reduced per CTA in
+        // shared memory, across CTAs through global memory.
         if (repair) {
-            if (own && mcode == BL_CODE_STALE) dirty[atomicAdd(&misc[M_NDIRTY], 1)] = tid;
+            uint64_t hz = bl_sortable(bl_add(now, bl_mul(win, P.repair_horizon)));
+            if (!(hz >= s_ts[0])) hz = s_ts[0];
+            const bool sel = own && mcode == BL_CODE_STALE && mts <= hz;
+            int li = -1;
+            if (sel) { li = atomicAdd(&misc[M_NDIRTY], 1); dirty[li] = tid; }
             __syncthreads();
             const int nd = misc[M_NDIRTY];
-            for (int d = warp; d < nd; d += nwarps) {
-                const int dt = dirty[d], dk = base + dt;
-                rescan_row(S.toi + (size_t)dk * (size_t)S.pitch, n, dk, lane, scratch + 2 * dt);
-            }
+            if (tid == 0) misc[M_SBASE] = (ncta > 1 && nd) ? (int)atomicAdd(P.bar + 4, (unsigned)nd) : 0;
             __syncthreads();
-            if (own && mcode == BL_CODE_STALE) { mts = scratch[2 * tid]; mcode = scratch[2 * tid + 1]; }
-            if (tid == 0) misc[M_NDIRTY] = 0;
+            const int sbase = misc[M_SBASE];
+            if (sel) {
+                __stcg(P.stale_list + 2 * (size_t)(sbase + li), (uint64_t)k);
+                __stcg(P.stale_list + 2 * (size_t)(sbase + li) + 1, (uint64_t)myseq);
+            }
+            sync_all(P, epoch);
+            const int total = ncta > 1 ? (int)__ldcg(P.bar + 4) : nd;
+            long long *q_seq = reinterpret_cast<long long *>(sm + L.stash);
+            unsigned long long *smin_ts = reinterpret_cast<unsigned long long *>(sm + L.stash + BL_RCHUNK);
+            int *q_k = reinterpret_cast<int *>(sm + L.stash + 2 * BL_RCHUNK);
+            int *smin_x = q_k + BL_RCHUNK;
+            int chunk = 0;
+            for (int q0 = 0; q0 < total; q0 += BL_RCHUNK, chunk++) {
+                const int cn = total - q0 < BL_RCHUNK ? total - q0 : BL_RCHUNK;
+                for (int e = tid; e < cn; e += T) {
+                    q_k[e] = (int)__ldcg(P.stale_list + 2 * (size_t)(q0 + e));
+                    q_seq[e] = (long long)__ldcg(P.stale_list + 2 * (size_t)(q0 + e) + 1);
+                    smin_ts[e] = ~0ull; smin_x[e] = 0x7fffffff;
+                }
+                __syncthreads();
+                for (int e0 = 0; e0 < cn; e0 += 16) {
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int e = e0 + u;
+                        const bool ok = own && e < cn && q_k[e] != k && myseq >= q_seq[e];
+                        v[u] = ok ? __ldcg(myrow + q_k[e]) : BL_INF;
+                    }
+                    unsigned hit = 0;
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        if (v[u] < BL_INF) {
+                            const unsigned long long ts = bl_sortable(v[u]);
+                            if (ts <= smin_ts[e0 + u]) { atomicMin(&smin_ts[e0 + u], ts); hit |= 1u << u; }
+                        }
+                    }
+                    __syncthreads();
+                    // ties: the smallest pair code = the smallest partner index
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        if ((hit >> u) & 1u)
+                            if (bl_sortable(v[u]) == smin_ts[e0 + u]) atomicMin(&smin_x[e0 + u], k);
+                }
+                __syncthreads();
+                if (ncta > 1) {
+                    uint64_t *const part = P.partial + ((size_t)(chunk & 1) * BL_MAX_CTAS + cta) * BL_RCHUNK * 2;
+                    for (int e = tid; e < cn; e += T) { __stcg(part + 2 * e, (uint64_t)smin_ts[e]); __stcg(part + 2 * e + 1, (uint64_t)(unsigned)smin_x[e]); }
+                    sync_all(P, epoch);
+                }
+                for (int d = warp; d < nd; d += nwarps) {
+                    const int e = sbase + d - q0;
+                    if (e < 0 || e >= cn) continue;
+                    uint64_t ts = ~0ull, xx = 0x7fffffffull;
+                    if (ncta > 1) {
+                        const uint64_t *const pbase = P.partial + (size_t)(chunk & 1) * BL_MAX_CTAS * BL_RCHUNK * 2;
+                        for (int c = lane; c < ncta; c += 32) {
+                            const uint64_t t2 = __ldcg(pbase + ((size_t)c * BL_RCHUNK + e) * 2);
+                            const uint64_t x2 = __ldcg(pbase + ((size_t)c * BL_RCHUNK + e) * 2 + 1);
+                            if (bl_key_less(t2, x2, ts, xx)) { ts = t2; xx = x2; }
+                        }
+                        const int w = warp_argmin(ts, xx);
+                        ts = __shfl_sync(0xffffffffu, ts, w);
+                        xx = __shfl_sync(0xffffffffu, xx, w);
+                    } else {
+                        ts = smin_ts[e]; xx = (uint64_t)(unsigned)smin_x[e];
+                    }
+                    if (lane == 0) { scratch[2 * dirty[d]] = ts; scratch[2 * dirty[d] + 1] = xx; }
+                }
+                __syncthreads();
+            }
+            if (sel) {
+                const uint64_t ts = scratch[2 * tid];
+                if (ts == ~0ull) { mts = ts_inf; mcode = BL_CODE_NONE; }
+                else { mts = ts; mcode = bl_pair_code(k, (int)scratch[2 * tid + 1]); }
+            }
+            if (tid == 0) { misc[M_NDIRTY] = 0; if (cta == 0 && ncta > 1) *(P.bar + 4) = 0; }
             if (prof_thread) { prof[3] += clock64() - c0; prof[4]++; n_rescans += nd; }
             __syncthreads();
             continue;
@@ -646,17 +706,14 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 const int r = j >> 1;
                 if (x < 0) continue;
                 if (r == myrank) {
-                    // toi_table[idx2][idx1] = INF, simulation.py:458 (the lower index stores both cells)
-                    if (x != k && k < x) {
-                        __stcg(myrow + x, BL_INF);
-                        __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
-                    }
+                    // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
+                    if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
                     continue;
                 }
                 if (mine && r < myrank) continue;  // that pair is re-solved at my (later) collision by x's owner
+                // my cell in the row of the ball whose collision is the later one of the pair
                 const double v = stash[(size_t)j * T + tid];
                 __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
-                __stcg(myrow + x, v);
                 if (x == q) partner_hit = true;
                 if (v < BL_INF) {
                     const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
@@ -674,6 +731,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 __stcg(S.p0x + k, p0x); __stcg(S.p0y + k, p0y); __stcg(S.vx + k, vx); __stcg(S.vy + k, vy);
                 __stcg(S.t0 + k, t0);
                 __stcg(S.obs_arg + k, c_oarg[tid]); __stcg(S.obs_idx + k, c_oidx[tid]);
+                myseq = seq_base + done + myrank + 1;
+                __stcg(S.seq + k, myseq);
             } else if (mcode == BL_CODE_STALE) {
                 if (c_code != BL_CODE_NONE && c_ts < mts) { mts = c_ts; mcode = c_code; }  // strictly earlier: decisive
             } else if (partner_hit) {
@@ -734,6 +793,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 #pragma unroll
         for (int q = 0; q < 8; q++) res->prof[q] = prof[q];
         res->window = win;
+        *S.seq_counter = seq_base + done;
     }
     if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 }
@@ -827,6 +887,8 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     // the window length found by the previous launch on this system is a good first guess
     P.window = (h->window_n == s->n && h->window_sys == (const void *)s->toi) ? h->window : 0.0;
     P.bar = h->d_bar; P.post = h->d_post; P.viol = h->d_viol;
+    P.stale_list = h->d_stale; P.partial = h->d_partial;
+    P.repair_horizon = h->repair_horizon;
     size_t smem = (size_t)make_layout(P.T, P.m_max, s->n_obstacles).words * 8;
     if (smem > h->max_smem_optin)
         return bl_set_error(h, BL_EUNSUPPORTED, "event kernel needs %zu B of shared memory per CTA (limit %zu)", smem,

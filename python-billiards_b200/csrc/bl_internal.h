@@ -19,6 +19,9 @@ struct bl_handle {
     unsigned *d_bar;          // grid barrier counter
     uint64_t *d_post;         // [2][BL_MAX_CTAS][BL_POST_WORDS] keys posted by each CTA
     uint64_t *d_viol;         // [2][BL_MAX_CTAS] earliest violating new key of each CTA
+    uint64_t *d_stale;        // [BL_MAX_CTAS * BL_MAX_THREADS][2] candidates under repair
+    uint64_t *d_partial;      // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
+    double repair_horizon;    // in windows (BL_REPAIR_HORIZON, default 8)
     // window length the last launch ended with, and the system it belongs to
     double window;
     int window_n;
@@ -33,6 +36,7 @@ struct bl_handle {
 #define BL_R_POST 6           // keys one CTA may post per round
 #define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
 #define BL_M_MAX 48           // collisions committed per round, at most
+#define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
 
 int bl_set_error(bl_handle *h, int code, const char *fmt, ...);
@@ -45,6 +49,7 @@ int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, in
 // bl_table.cu
 int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st);
 int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st);
+int bl_launch_symmetrize(bl_handle *h, const bl_system *s, cudaStream_t st);
 int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_t *d_idx, cudaStream_t st);
 int bl_launch_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
                           cudaStream_t st);

@@ -3,6 +3,8 @@
 //   bl_recompute_kernel      add_ball's new row (simulation.py:176-209) and recompute_toi (:266-281): for each listed
 //                            ball, every pair with it is re-solved at the current time and stored in both triangles of
 //                            the symmetric table; its next-obstacle entry is refreshed.
+//   bl_symmetrize_kernel     the event kernel rewrites only the row of a colliding ball; this pass copies every
+//                            current cell (row of the ball with the larger sequence number) onto its mirror.
 //   bl_rebuild_cover_kernel  per-ball candidate minima for the event kernel (full-row minimum, one warp per row).
 //   bl_row_minima_kernel     the reference-shaped _balls_toi/_balls_idx (:85-86, :184-191): minimum of the lower
 //                            triangle row, first index on ties, column 0 for an all-inf row, (inf,-1) for row 0.
@@ -45,6 +47,46 @@ __device__ __forceinline__ void warp_min_key(uint64_t &ts, uint64_t &cd) {
     for (int o = 16; o > 0; o >>= 1) {
         const uint64_t t2 = __shfl_xor_sync(0xffffffffu, ts, o), c2 = __shfl_xor_sync(0xffffffffu, cd, o);
         if (bl_key_less(t2, c2, ts, cd)) { ts = t2; cd = c2; }
+    }
+}
+
+// one 32x32 tile pair (bi <= bj) per block: tile A = rows of block bi x columns of block bj, tile B its mirror
+__global__ void __launch_bounds__(256) bl_symmetrize_kernel(const bl_system S) {
+    __shared__ double A[32][33], B[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bi > bj) return;
+    const int tx = threadIdx.x, ty = threadIdx.y, n = S.n;
+    const size_t pitch = (size_t)S.pitch;
+    const bool diag = bi == bj;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        A[r][tx] = (i < n && j < n) ? S.toi[(size_t)i * pitch + j] : BL_INF;
+        if (!diag) {
+            const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+            B[r][tx] = (i2 < n && j2 < n) ? S.toi[(size_t)i2 * pitch + j2] : BL_INF;
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i >= n || j >= n || (diag && r >= tx)) continue;
+        const long long si = S.seq[i], sj = S.seq[j];
+        if (diag) {
+            if (si > sj) A[tx][r] = A[r][tx];
+            else if (sj > si) A[r][tx] = A[tx][r];
+        } else {
+            if (si > sj) B[tx][r] = A[r][tx];
+            else if (sj > si) A[r][tx] = B[tx][r];
+        }
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        if (i < n && j < n) S.toi[(size_t)i * pitch + j] = A[r][tx];
+        if (!diag) {
+            const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+            if (i2 < n && j2 < n) S.toi[(size_t)i2 * pitch + j2] = B[r][tx];
+        }
     }
 }
 
@@ -128,6 +170,14 @@ int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int
         h->launches++;
     }
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_recompute_kernel");
+}
+
+int bl_launch_symmetrize(bl_handle *h, const bl_system *s, cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    const unsigned nb = (unsigned)((s->n + 31) / 32);
+    bl_symmetrize_kernel<<<dim3(nb, nb, 1), dim3(32, 8, 1), 0, st>>>(*s);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_symmetrize_kernel");
 }
 
 int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st) {
