@@ -45,7 +45,7 @@ class BlResult(ctypes.Structure):
                 ("bo_t", ctypes.c_double), ("bo_ball", ctypes.c_int64), ("bo_obs", ctypes.c_int64),
                 ("bo_arg", ctypes.c_double), ("status", ctypes.c_int32), ("stop", ctypes.c_int32),
                 ("n_logged", ctypes.c_int64), ("n_rescans", ctypes.c_int64), ("err_i", ctypes.c_int64),
-                ("err_j", ctypes.c_int64), ("prof", ctypes.c_int64 * 8), ("window", ctypes.c_double)]
+                ("err_j", ctypes.c_int64), ("prof", ctypes.c_int64 * 16), ("window", ctypes.c_double)]
 
 
 class BlLog(ctypes.Structure):

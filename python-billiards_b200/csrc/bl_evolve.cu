@@ -14,35 +14,39 @@
 // times of its two balls) comes earlier than e2.  That condition can be CHECKED exactly, so a round works on a
 // whole window of pending collisions at once:
 //
-//   1. post      every ball owner whose candidate key (time, code) lies below the window end `theta` posts it;
-//                one grid barrier later every CTA holds the same complete list of keys < theta, sorts it and
-//                cuts it at the first entry that shares a ball with an earlier one (or is only a lower bound);
-//   2. resolve   one thread per listed collision computes the new velocities (elastic_collision / obstacle);
-//   3. solve     every owner solves its pair with every ball of the batch -- with its state as of just before
-//                that collision -- and parks the values in shared memory; any new key that would come earlier
+//   1. post      every ball whose candidate key (time, code) lies below the window end `theta` is posted; one
+//                grid barrier later every CTA holds the same complete list of keys < theta;
+//   2. analyse   warp 0 sorts the list in registers and cuts it at the first entry that shares a ball with an
+//                earlier one (or is only a lower bound); one lane per remaining collision resolves it
+//                (elastic_collision / obstacle reflection);
+//   3. solve     every ball is solved against every ball of the batch -- with its state as of just before that
+//                collision -- and the values are parked in shared memory; any new key that would come earlier
 //                than a collision of the batch is a violation;
 //   4. commit    the batch prefix below the earliest violation (all of it, normally) is committed: table rows
-//                and columns stored, candidates folded, states updated, log written.  The rest is re-posted.
+//                stored, candidates folded, states updated, log written.  The rest is re-posted.
 //
 // Collision 1 of a round is the true global minimum, so every round commits at least what the reference's
 // iteration would; the committed sequence, every table entry and every state bit are the reference's.
 //
-// Data placement: a ball is owned by one thread; its state of record (p0, v, t0) and candidate keys live in
-// that thread's registers for the whole launch (mirrored to global memory when they change, so that resolvers
-// can read any ball); the table of absolute impact times stays in HBM and a collision only WRITES it: the whole
-// row of each colliding ball, coalesced.  The mirrored cells (column of the colliding ball) are left outdated --
-// a per-ball sequence number says which of toi[i][j] / toi[j][i] is current (the row of the ball whose collision
-// came later) and bl_symmetrize makes both current again before anything on the host side reads the table.  The
+// Data placement: a CTA owns Tb consecutive balls; their state of record (p0, v, t0), candidate keys and
+// next-obstacle entries live in its shared memory for the whole launch (mirrored to global memory when they
+// change, so that resolvers can read any ball).  H threads serve each ball (thread = helper h of ball b): the
+// per-ball bookkeeping is done by helper 0, the pair solves, table stores and repair loads of a round are split
+// between the helpers -- with one warp per scheduler the FP64 dependency chains would otherwise sit exposed.
+// The table of absolute impact times stays in HBM and a collision only WRITES it: the whole row of each
+// colliding ball, coalesced.  The mirrored cells (column of the colliding ball) are left outdated -- a per-ball
+// sequence number says which of toi[i][j] / toi[j][i] is current (the row of the ball whose collision came
+// later) and bl_symmetrize makes both current again before anything on the host side reads the table.  The
 // kernel reads the table only to repair stale candidates.
-// Grid: ceil(N/T) CTAs, one per SM; <= 16 CTAs run as one thread-block cluster (hardware barrier), more use a
+// Grid: ceil(N/Tb) CTAs, one per SM; <= 16 CTAs run as one thread-block cluster (hardware barrier), more use a
 // cooperative launch with a global-memory barrier.
 //
 // "Cover" instead of row minima: ball k's candidate m[k] is the minimum over a SUBSET of row k that
 // always contains every pair whose value was last written at an event of the OTHER ball.  After an event of ball
-// a every pair (a,k) is re-solved and folded into m[k] by k's owner, so m[a] is simply emptied.  If k's
-// candidate was its pair with a and the new value is larger, m[k] keeps the old time as a lower bound ("stale");
-// stale rows are re-read from the table only when one of them reaches the front of the queue.  The global
-// minimum over {m[k]} equals the minimum over the whole table.
+// a every pair (a,k) is re-solved and folded into m[k], so m[a] is simply emptied.  If k's candidate was its
+// pair with a and the new value is larger, m[k] keeps the old time as a lower bound ("stale"); stale candidates
+// are made exact again only when they come near the front of the queue.  The global minimum over {m[k]} equals
+// the minimum over the whole table.
 #include <cstdio>
 
 #include "bl_arith.cuh"
@@ -53,9 +57,8 @@ namespace {
 enum { MODE_WINDOW = 0, MODE_ARGMIN = 1 };
 enum { KIND_BOTH = 0, KIND_BB = 1, KIND_BO = 2 };
 enum { SYNC_CTA = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
-
-// flags of a collected entry
-enum { F_DUP = 1, F_CONFLICT = 2, F_STALE = 4 };
+enum { F_DUP = 1, F_CONFLICT = 2 };
+enum { ACT_BATCH = 0, ACT_OVERFLOW, ACT_EMPTY, ACT_REPAIR, ACT_STOP, ACT_ERROR };
 
 struct Params {
     bl_system s;
@@ -65,13 +68,14 @@ struct Params {
     int query_only;
     bl_log log;
     bl_result *result;
-    int T;          // threads per CTA = balls per CTA
+    int Tb;         // balls per CTA
+    int H;          // threads per ball
     int ncta;
     int m_max;      // collisions per round the stash has room for
     int target;     // collisions per round the window aims at
     int sync_mode;
     double window;  // initial window length (0: unknown)
-    unsigned *bar;  // grid barrier counter (zero at launch)
+    unsigned *bar;  // [0] grid barrier counter, [4] stale-list length (zero at launch)
     uint64_t *post; // [2][BL_MAX_CTAS][BL_POST_WORDS]
     uint64_t *viol; // [2][BL_MAX_CTAS]
     uint64_t *stale_list; // [BL_MAX_CTAS * BL_MAX_THREADS][2] (ball, seq) of the candidates under repair
@@ -81,47 +85,59 @@ struct Params {
 
 // ---- shared memory map (8-byte words) -----------------------------------------------------------------
 struct Layout {
-    int stash;                        // [2*m_max][T] doubles
+    int stash;                        // [2*m_max][Tb] doubles (repair scratch while no batch is in flight)
     int bx, by, bvx, bvy, bt;         // [2*m_max] batch balls: state right after their collision
     int bid, brc;                     // [2*m_max] ints: ball index (-1: none), radius class
     int e_ts, e_code;                 // [BL_EV_CAP] collected keys (unsorted)
-    int s_ts, s_code, s_flag;         // [BL_EV_CAP] sorted keys, flags (int)
+    int s_ts, s_code;                 // [32] sorted keys
+    int s_flag, a_rank, a_flag;       // [32] ints: flags in sorted order; rank and flags by collection slot
     int r_pay;                        // [m_max][13] log payload per rank
     int r_info;                       // [m_max][4] ints: status, obstacle index, is ball-ball, pad
     int pl_ts, pl_code;               // [BL_R_POST] this CTA's posted keys
     int w_ts, w_code;                 // [32] warp slots of the exact argmin
-    int mass, radius, oarg;           // [T] doubles
-    int oidx, brank;                  // [T] ints
-    int dirty;                        // [T] ints
-    int scratch;                      // [2*T] repair results (ts, code) / new obstacle entry
+    int p0x, p0y, vx, vy, t0;         // [Tb] state of record of my balls
+    int mts, mcode, ots;              // [Tb] candidate key, next-obstacle time (sortable)
+    int seq;                          // [Tb] sequence number of the ball's last collision
+    int mass, radius, oarg;           // [Tb] doubles
+    int oidx, brank, rclass;          // [Tb] ints
+    int dirty;                        // [Tb] ints
+    int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
+    int fold;                         // [H][Tb][2] partial candidate of each helper + [H][Tb] ints partner-hit
+    int wq;                           // [T/32][4*BL_WQ_CAP] per-warp queue of pairs that reach the sqrt
     int obs;                          // 5 * n_obs
     int misc;                         // 32 words
     int words;
 };
-__host__ __device__ inline Layout make_layout(int T, int m_max, int n_obs) {
+__host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_obs) {
     Layout L;
     int w = 0;
-    L.stash = w; w += 2 * m_max * T;
+    L.stash = w; w += 2 * m_max * Tb;
     L.bx = w; w += 2 * m_max; L.by = w; w += 2 * m_max; L.bvx = w; w += 2 * m_max; L.bvy = w; w += 2 * m_max;
     L.bt = w; w += 2 * m_max;
     L.bid = w; w += m_max; L.brc = w; w += m_max;
     L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP;
-    L.s_ts = w; w += BL_EV_CAP; L.s_code = w; w += BL_EV_CAP; L.s_flag = w; w += BL_EV_CAP / 2;
+    L.s_ts = w; w += 32; L.s_code = w; w += 32;
+    L.s_flag = w; w += 16; L.a_rank = w; w += 16; L.a_flag = w; w += 16;
     L.r_pay = w; w += 13 * m_max;
     L.r_info = w; w += 2 * m_max;
     L.pl_ts = w; w += BL_R_POST; L.pl_code = w; w += BL_R_POST;
     L.w_ts = w; w += 32; L.w_code = w; w += 32;
-    L.mass = w; w += T; L.radius = w; w += T; L.oarg = w; w += T;
-    L.oidx = w; w += (T + 1) / 2; L.brank = w; w += (T + 1) / 2;
-    L.dirty = w; w += (T + 1) / 2;
-    L.scratch = w; w += 2 * T;
+    L.p0x = w; w += Tb; L.p0y = w; w += Tb; L.vx = w; w += Tb; L.vy = w; w += Tb; L.t0 = w; w += Tb;
+    L.mts = w; w += Tb; L.mcode = w; w += Tb; L.ots = w; w += Tb;
+    L.seq = w; w += Tb;
+    L.mass = w; w += Tb; L.radius = w; w += Tb; L.oarg = w; w += Tb;
+    L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += (Tb + 1) / 2; L.rclass = w; w += (Tb + 1) / 2;
+    L.dirty = w; w += (Tb + 1) / 2;
+    L.scratch = w; w += 3 * Tb;
+    L.fold = w; w += H * Tb * 2 + (H * Tb + 1) / 2;
+    L.wq = w; w += ((Tb * H) / 32) * 4 * BL_WQ_CAP;
     L.obs = w; w += 5 * (n_obs > 0 ? n_obs : 1);
     L.misc = w; w += 32;
     L.words = w;
     return L;
 }
 // ints of `misc`; M_VIOL is a 64-bit word index
-enum { M_PCOUNT = 0, M_ECOUNT, M_OVERFLOW, M_CUT, M_NDIRTY, M_ERRRANK, M_SBASE };
+enum { M_PCOUNT = 0, M_ECOUNT, M_NDIRTY, M_SBASE, M_ACTION, M_NF, M_NE, M_STOPKIND, M_STATUS };
 enum { M_VIOL = 8 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -172,6 +188,7 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
     const unsigned lo = __reduce_min_sync(FULL, (unsigned)(v >> 32) == hi ? (unsigned)v : 0xffffffffu);
     return ((uint64_t)hi << 32) | lo;
 }
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 __device__ __forceinline__ double as_d(uint64_t u) { return __longlong_as_double((long long)u); }
 __device__ __forceinline__ uint64_t as_u(double d) { return (uint64_t)__double_as_longlong(d); }
@@ -192,60 +209,79 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     extern __shared__ __align__(16) uint64_t sm[];
     const bl_system &S = P.s;
     const int n = S.n, K = S.n_classes, n_obs = S.n_obstacles;
-    const int T = P.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int Tb = P.Tb, H = P.H, T = Tb * H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int h = tid / Tb, bl = tid - h * Tb;  // helper h of local ball bl
+    const bool primary = h == 0;
     const int cta = blockIdx.x, ncta = P.ncta, m_max = P.m_max;
-    const Layout L = make_layout(T, m_max, n_obs);
+    const Layout L = make_layout(Tb, H, m_max, n_obs);
     double *stash = reinterpret_cast<double *>(sm + L.stash);
     double *bx = reinterpret_cast<double *>(sm + L.bx), *by = reinterpret_cast<double *>(sm + L.by);
     double *bvx = reinterpret_cast<double *>(sm + L.bvx), *bvy = reinterpret_cast<double *>(sm + L.bvy);
     double *bt = reinterpret_cast<double *>(sm + L.bt);
     int *bid = reinterpret_cast<int *>(sm + L.bid), *brc = reinterpret_cast<int *>(sm + L.brc);
     uint64_t *e_ts = sm + L.e_ts, *e_code = sm + L.e_code, *s_ts = sm + L.s_ts, *s_code = sm + L.s_code;
-    int *s_flag = reinterpret_cast<int *>(sm + L.s_flag);
+    int *s_flag = reinterpret_cast<int *>(sm + L.s_flag), *a_rank = reinterpret_cast<int *>(sm + L.a_rank);
+    int *a_flag = reinterpret_cast<int *>(sm + L.a_flag);
     double *r_pay = reinterpret_cast<double *>(sm + L.r_pay);
     int *r_info = reinterpret_cast<int *>(sm + L.r_info);
     uint64_t *pl_ts = sm + L.pl_ts, *pl_code = sm + L.pl_code, *w_ts = sm + L.w_ts, *w_code = sm + L.w_code;
+    double *st_p0x = reinterpret_cast<double *>(sm + L.p0x), *st_p0y = reinterpret_cast<double *>(sm + L.p0y);
+    double *st_vx = reinterpret_cast<double *>(sm + L.vx), *st_vy = reinterpret_cast<double *>(sm + L.vy);
+    double *st_t0 = reinterpret_cast<double *>(sm + L.t0);
+    uint64_t *c_mts = sm + L.mts, *c_mcode = sm + L.mcode, *c_ots = sm + L.ots;
+    long long *c_seq = reinterpret_cast<long long *>(sm + L.seq);
     double *c_mass = reinterpret_cast<double *>(sm + L.mass), *c_radius = reinterpret_cast<double *>(sm + L.radius);
     double *c_oarg = reinterpret_cast<double *>(sm + L.oarg);
     int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *brank = reinterpret_cast<int *>(sm + L.brank);
+    int *c_rclass = reinterpret_cast<int *>(sm + L.rclass);
     int *dirty = reinterpret_cast<int *>(sm + L.dirty);
     uint64_t *scratch = sm + L.scratch;
+    uint64_t *fold = sm + L.fold;
+    int *fold_hit = reinterpret_cast<int *>(sm + L.fold + H * Tb * 2);
+    double *wq = reinterpret_cast<double *>(sm + L.wq);
     const bl_obstacle *obs = reinterpret_cast<const bl_obstacle *>(sm + L.obs);
     int *misc = reinterpret_cast<int *>(sm + L.misc);
     unsigned long long *m_viol = reinterpret_cast<unsigned long long *>(sm + L.misc + M_VIOL);
 
-    const int base = cta * T;
-    const int k = base + tid;  // the ball this thread owns
+    const int base = cta * Tb;
+    const int k = base + bl;  // the ball this thread serves
     const bool own = k < n;
 
     // ---- load the resident state --------------------------------------------------------------
+    const uint64_t ts_inf = bl_sortable(BL_INF);
     for (int q = tid; q < 5 * n_obs; q += T) sm[L.obs + q] = reinterpret_cast<const uint64_t *>(S.obstacles)[q];
-    double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0;
-    uint64_t mts = bl_sortable(BL_INF), mcode = BL_CODE_NONE, ots = bl_sortable(BL_INF);
-    int myrc = 0;
-    long long myseq = 0;  // sequence number of my last collision: toi[k][x] is current for every x with seq[x] <= myseq
     const long long seq_base = *S.seq_counter;
-    if (own) {
-        myseq = S.seq[k];
-        p0x = S.p0x[k]; p0y = S.p0y[k]; vx = S.vx[k]; vy = S.vy[k]; t0 = S.t0[k];
-        myrc = S.rclass[k];
-        c_mass[tid] = S.mass[k];
-        c_radius[tid] = S.radius[k];
-        c_oarg[tid] = S.obs_arg[k];
-        c_oidx[tid] = S.obs_idx[k];
-        ots = bl_sortable(S.obs_t[k]);
-        mts = bl_sortable(S.cover_t[k]);
-        mcode = S.cover_code[k];
+    if (primary) {
+        if (own) {
+            st_p0x[bl] = S.p0x[k]; st_p0y[bl] = S.p0y[k]; st_vx[bl] = S.vx[k]; st_vy[bl] = S.vy[k]; st_t0[bl] = S.t0[k];
+            c_seq[bl] = S.seq[k];
+            c_rclass[bl] = S.rclass[k];
+            c_mass[bl] = S.mass[k];
+            c_radius[bl] = S.radius[k];
+            c_oarg[bl] = S.obs_arg[k];
+            c_oidx[bl] = S.obs_idx[k];
+            c_ots[bl] = bl_sortable(S.obs_t[k]);
+            c_mts[bl] = bl_sortable(S.cover_t[k]);
+            c_mcode[bl] = S.cover_code[k];
+        } else {
+            st_p0x[bl] = 0; st_p0y[bl] = 0; st_vx[bl] = 0; st_vy[bl] = 0; st_t0[bl] = 0;
+            c_seq[bl] = 0; c_rclass[bl] = 0; c_mass[bl] = 0; c_radius[bl] = 0; c_oarg[bl] = 0; c_oidx[bl] = -1;
+            c_ots[bl] = ts_inf; c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE;
+        }
+        brank[bl] = -1;
     }
-    brank[tid] = -1;
     const double rs11 = (K == 1 && n > 0) ? S.rsum2[0] : 0.0;
     double *const myrow = S.toi + (size_t)(own ? k : 0) * (size_t)S.pitch;
     if (tid < 32) sm[L.misc + tid] = 0;
+    if (tid < BL_R_POST) { pl_ts[tid] = ~0ull; pl_code[tid] = BL_CODE_END; }
+    if (tid < 32) { a_rank[tid] = 0; a_flag[tid] = 0; }
     __syncthreads();
-    if (tid == 0) { misc[M_CUT] = BL_EV_CAP; misc[M_ERRRANK] = BL_EV_CAP; *m_viol = ~0ull; }
+    if (tid == 0) *m_viol = ~0ull;
+    const int myrc = c_rclass[bl];
 
-    const bool prof_thread = tid == 0;
-    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof_thread = warp == 0;  // the whole warp reads the clock: a single-lane branch would leave warp 0 diverged
+    long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long done = 0, n_bb = 0, n_rescans = 0;
     double now = P.time;   // Billiard.time: time of the last committed collision
     double prev_now = P.time;
@@ -259,9 +295,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     const bool want_log = P.log.cap > 0;
     bl_result *const res = P.result;
     // exclusive upper bound of the keys that may be processed: t <= end_time and t < inf
-    const uint64_t ts_inf = bl_sortable(BL_INF);
     uint64_t end_excl = bl_sortable(P.end_time);
     end_excl = end_excl >= ts_inf ? ts_inf : end_excl + 1;
+    const unsigned lt_mask = (1u << lane) - 1u;
     __syncthreads();
     if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 
@@ -274,28 +310,31 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             theta = bl_sortable(bl_add(now, win));
             if (theta > end_excl) theta = end_excl;
         }
-        uint64_t kts = ~0ull, kcode = BL_CODE_END;
-        if (own) {
-            if (kindmask != KIND_BO) { kts = mts; kcode = mcode; }
-            if (kindmask != KIND_BB) {
-                const uint64_t oc = BL_CODE_OBS | (uint64_t)k;
-                if (kindmask == KIND_BO || bl_key_less(ots, oc, kts, kcode)) { kts = ots; kcode = oc; }
+        if (warp < (Tb >> 5)) {  // the primaries' warps
+            uint64_t kts = ~0ull, kcode = BL_CODE_END;
+            if (own) {
+                if (kindmask != KIND_BO) { kts = c_mts[bl]; kcode = c_mcode[bl]; }
+                if (kindmask != KIND_BB) {
+                    const uint64_t ots = c_ots[bl], oc = BL_CODE_OBS | (uint64_t)k;
+                    if (kindmask == KIND_BO || bl_key_less(ots, oc, kts, kcode)) { kts = ots; kcode = oc; }
+                }
+            }
+            if (mode == MODE_WINDOW) {
+                if (own && kts < theta) {
+                    const int s = atomicAdd(&misc[M_PCOUNT], 1);
+                    if (s < BL_R_POST) { pl_ts[s] = kts; pl_code[s] = kcode; }
+                }
+            } else {
+                const int w = warp_argmin(kts, kcode);
+                if (lane == w) { w_ts[warp] = kts; w_code[warp] = kcode; }
             }
         }
-        if (mode == MODE_WINDOW) {
-            if (own && kts < theta) {
-                const int s = atomicAdd(&misc[M_PCOUNT], 1);
-                if (s < BL_R_POST) { pl_ts[s] = kts; pl_code[s] = kcode; }
-            }
-            __syncthreads();
-        } else {
-            const int w = warp_argmin(kts, kcode);
-            if (lane == w) { w_ts[warp] = kts; w_code[warp] = kcode; }
-            __syncthreads();
+        __syncthreads();
+        if (mode == MODE_ARGMIN) {
             if (warp == 0) {
                 uint64_t ts = ~0ull, cd = BL_CODE_END;
-                if (lane < nwarps) { ts = w_ts[lane]; cd = w_code[lane]; }
-                const int w2 = nwarps > 1 ? warp_argmin(ts, cd) : 0;
+                if (lane < (Tb >> 5)) { ts = w_ts[lane]; cd = w_code[lane]; }
+                const int w2 = Tb > 32 ? warp_argmin(ts, cd) : 0;
                 if (lane == w2) { pl_ts[0] = ts; pl_code[0] = cd; misc[M_PCOUNT] = cd != BL_CODE_END ? 1 : 0; }
             }
             __syncthreads();
@@ -306,126 +345,215 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             uint64_t word;
             if (tid == 0) word = pack2(pc < BL_R_POST ? pc : BL_R_POST, pc > BL_R_POST ? 1 : 0);
             else word = (tid & 1) ? pl_ts[(tid - 1) >> 1] : pl_code[(tid - 1) >> 1];
-            __stcg(post + tid, word);
+            __stcg(post + (tid ? tid + 1 : 0), word);  // header in word 0, key e in words 2+2e, 3+2e (16-byte aligned)
         }
+        long long cb = 0;
+        if (prof_thread) cb = clock64();
         sync_all(P, epoch);
+        if (prof_thread) { const long long ce = clock64(); prof[8] += cb - c0; prof[9] += ce - cb; c0 = ce; }
         // =========================== 2. collect ==============================================================
         {
             const uint64_t *const box = P.post + (size_t)par * BL_MAX_CTAS * BL_POST_WORDS;
             for (int c = tid; c < ncta; c += T) {
                 const uint64_t *rec = box + (size_t)c * BL_POST_WORDS;
+                // one trip: header and the first two keys (a CTA rarely posts more)
                 const uint64_t hd = __ldcg(rec);
+                const ulonglong2 k0 = __ldcg(reinterpret_cast<const ulonglong2 *>(rec + 2));
+                const ulonglong2 k1 = __ldcg(reinterpret_cast<const ulonglong2 *>(rec + 4));
                 const int cnt = lo32(hd);
-                if (hi32(hd)) misc[M_OVERFLOW] = 1;
-                for (int e = 0; e < cnt; e++) {
-                    const int slot = atomicAdd(&misc[M_ECOUNT], 1);
-                    if (slot < BL_EV_CAP) { e_ts[slot] = __ldcg(rec + 1 + 2 * e); e_code[slot] = __ldcg(rec + 2 + 2 * e); }
-                    else misc[M_OVERFLOW] = 1;
+                if (hi32(hd)) misc[M_ACTION] = ACT_OVERFLOW;
+                if (cnt > 0) {
+                    const int slot = atomicAdd(&misc[M_ECOUNT], cnt);
+                    if (slot < BL_EV_CAP) { e_ts[slot] = k0.x; e_code[slot] = k0.y; }
+                    if (cnt > 1 && slot + 1 < BL_EV_CAP) { e_ts[slot + 1] = k1.x; e_code[slot + 1] = k1.y; }
+                    for (int e = 2; e < cnt; e++)
+                        if (slot + e < BL_EV_CAP) { e_ts[slot + e] = __ldcg(rec + 2 + 2 * e); e_code[slot + e] = __ldcg(rec + 3 + 2 * e); }
                 }
             }
         }
         par ^= 1;
         __syncthreads();
-        const int nE = misc[M_ECOUNT];
-        const bool overflow = misc[M_OVERFLOW] != 0;
+        if (prof_thread) prof[11] += clock64() - c0;
+
+        // =========================== 3. analyse + resolve ======================================================
+        // order and conflicts of the collected keys, one (i, j) pair per thread: entry j comes before entry i ->
+        // rank[i]++; and if they share a ball, i is a duplicate (same pair, posted by both balls) or a conflict
+        {
+            const int nr = misc[M_ECOUNT];
+            if (mode == MODE_WINDOW && nr > 1 && nr <= 32) {
+                for (int p = tid; p < nr * nr; p += T) {
+                    const int i = p / nr, j = p - i * nr;
+                    const uint64_t ti = e_ts[i], ci = e_code[i], tj = e_ts[j], cj = e_code[j];
+                    if (i != j && (bl_key_less(tj, cj, ti, ci) || (tj == ti && cj == ci && j < i))) {
+                        atomicAdd(&a_rank[i], 1);
+                        int a, b, a2, b2;
+                        key_balls(ci, a, b);
+                        key_balls(cj, a2, b2);
+                        if (a >= 0 && a2 >= 0) {
+                            if (a2 == a && b2 == b) atomicOr(&a_flag[i], F_DUP);
+                            else if (a2 == a || a2 == b || (b2 >= 0 && (b2 == a || b2 == b))) atomicOr(&a_flag[i], F_CONFLICT);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (warp == 0) {
+            __syncwarp();
+            int nE = misc[M_ECOUNT];
+            int action = misc[M_ACTION] == ACT_OVERFLOW ? ACT_OVERFLOW : ACT_BATCH;
+            int stop_kind = 0, st_status = BL_OK, nf = 0;
+            uint64_t ts = ~0ull, cd = BL_CODE_END;
+            if (mode == MODE_ARGMIN) {
+                // only the smallest of the per-CTA minima is known to be next
+                for (int i = lane; i < nE && i < BL_EV_CAP; i += 32)
+                    if (bl_key_less(e_ts[i], e_code[i], ts, cd)) { ts = e_ts[i]; cd = e_code[i]; }
+                const int w = warp_argmin(ts, cd);
+                ts = shfl_u64(ts, w); cd = shfl_u64(cd, w);
+                if (lane != 0) { ts = ~0ull; cd = BL_CODE_END; }
+                nE = nE > 0 ? 1 : 0;
+            } else {
+                if (nE > 32) action = ACT_OVERFLOW;
+                else if (lane < nE) { ts = e_ts[lane]; cd = e_code[lane]; }
+            }
+            const bool max_reached = P.max_events >= 0 && done >= P.max_events;
+            if (action == ACT_OVERFLOW) {
+            } else if (nE == 0) {
+                if (final_stage == 0 && !max_reached && mode == MODE_WINDOW && theta < end_excl) action = ACT_EMPTY;
+                else { action = ACT_STOP; stop_kind = max_reached ? BL_STOP_EVENTS : BL_STOP_TIME; }
+                if (lane == 0) { s_ts[0] = ts_inf; s_code[0] = BL_CODE_END; }
+            } else {
+                // ---- into sorted order (ranks and flags come from the pair pass) ----
+                int fl = 0;
+                if (nE > 1) {
+                    if (lane < nE) { const int rk = a_rank[lane]; s_ts[rk] = ts; s_code[rk] = cd; s_flag[rk] = a_flag[lane]; }
+                    __syncwarp();
+                    if (lane < nE) { ts = s_ts[lane]; cd = s_code[lane]; fl = s_flag[lane]; }
+                }
+                int a, b;
+                key_balls(cd, a, b);
+                const bool stale = lane < nE && cd == BL_CODE_STALE;
+                const bool dup = (fl & F_DUP) != 0, conflict = (fl & F_CONFLICT) != 0;
+                if (prof_thread) prof[14] += clock64() - c0;
+                const unsigned cutmask = __ballot_sync(0xffffffffu, lane < nE && (stale || conflict));
+                const int cut = cutmask ? __ffs(cutmask) - 1 : nE;
+                const uint64_t ts0 = shfl_u64(ts, 0);
+                if (final_stage == 0 && max_reached) {
+                    action = ACT_STOP; stop_kind = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
+                } else if (cut == 0) {
+                    action = ACT_REPAIR;  // the front entry is only a lower bound (it cannot be a conflict)
+                } else if (final_stage != 0) {
+                    action = ACT_STOP; stop_kind = BL_STOP_TIME;  // query rounds only look at the front entry
+                } else if (ts0 == BL_TS_NAN) {
+                    action = ACT_STOP; stop_kind = BL_STOP_ERROR; st_status = BL_ENAN;
+                } else if (ts0 >= end_excl) {
+                    action = ACT_STOP; stop_kind = BL_STOP_TIME;
+                } else if (want_log && done >= P.log.cap) {
+                    action = ACT_STOP; stop_kind = BL_STOP_LOG;
+                } else {
+                    long long allowed = mode == MODE_ARGMIN ? 1 : m_max;
+                    if (P.max_events >= 0 && P.max_events - done < allowed) allowed = P.max_events - done;
+                    if (want_log && P.log.cap - done < allowed) allowed = P.log.cap - done;
+                    const bool valid = lane < cut && !dup && ts < end_excl;
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    const int r = __popc(vm & lt_mask);
+                    nf = __popc(vm);
+                    if (nf > allowed) nf = (int)allowed;
+                    // ---- resolve: one lane per collision of the batch (rank r) ----
+                    int st = BL_OK;
+                    if (valid && r < nf) {
+                        const double t = bl_unsortable(ts);
+                        double *pl = r_pay + 13 * r;
+                        if (cd & BL_CODE_OBS) {
+                            // ball-obstacle, simulation.py:504-519 + :604-636
+                            const double q0x = __ldcg(S.p0x + a), q0y = __ldcg(S.p0y + a), wvx = __ldcg(S.vx + a), wvy = __ldcg(S.vy + a);
+                            const double wt0 = __ldcg(S.t0 + a), qarg = __ldcg(S.obs_arg + a);
+                            const int oi = __ldcg(S.obs_idx + a);
+                            const int rca = S.rclass[a];
+                            const double ax = bl_advance(q0x, wvx, t, wt0), ay = bl_advance(q0y, wvy, t, wt0);
+                            double nvx = wvx, nvy = wvy;
+                            st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, wvx, wvy, qarg, nvx, nvy) : BL_EASSERT;
+                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t;
+                            bid[2 * r] = a; brc[2 * r] = rca;
+                            bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
+                            pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
+                            pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
+                            r_info[4 * r] = st; r_info[4 * r + 1] = oi; r_info[4 * r + 2] = 0;
+                            if (a >= base && a < base + Tb) brank[a - base] = r;
+                        } else {
+                            // ball-ball, simulation.py:446-455 + :562-602 (a = idx1 < b = idx2)
+                            const double a0x = __ldcg(S.p0x + a), a0y = __ldcg(S.p0y + a), a_vx = __ldcg(S.vx + a), a_vy = __ldcg(S.vy + a);
+                            const double a_t0 = __ldcg(S.t0 + a);
+                            const double b0x = __ldcg(S.p0x + b), b0y = __ldcg(S.p0y + b), b_vx = __ldcg(S.vx + b), b_vy = __ldcg(S.vy + b);
+                            const double b_t0 = __ldcg(S.t0 + b);
+                            double m1 = S.mass[a], m2 = S.mass[b];
+                            const int rca = S.rclass[a], rcb = S.rclass[b];
+                            const double ax = bl_advance(a0x, a_vx, t, a_t0), ay = bl_advance(a0y, a_vy, t, a_t0);
+                            const double bxx = bl_advance(b0x, b_vx, t, b_t0), byy = bl_advance(b0y, b_vy, t, b_t0);
+                            bl_remap_masses(m1, m2);
+                            double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
+                            st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
+                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t;
+                            bid[2 * r] = a; brc[2 * r] = rca;
+                            bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
+                            bid[2 * r + 1] = b; brc[2 * r + 1] = rcb;
+                            pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
+                            pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
+                            r_info[4 * r] = st; r_info[4 * r + 1] = -1; r_info[4 * r + 2] = 1;
+                            if (a >= base && a < base + Tb) brank[a - base] = r;
+                            if (b >= base && b < base + Tb) brank[b - base] = r;
+                        }
+                    }
+                    if (prof_thread) prof[15] += clock64() - c0;
+                    // a collision that cannot be resolved (physics.py:277-279 / zero masses): commit what comes
+                    // before it; if it is the front one, stop with the reference's error
+                    const int er = __reduce_min_sync(0xffffffffu, (valid && r < nf && st != BL_OK) ? r : 0x7fffffff);
+                    if (er < nf) nf = er;
+                    if (nf == 0) action = ACT_ERROR;
+                }
+                if (lane == 0) { s_ts[0] = ts; s_code[0] = cd; }  // the front entry, for the stop stages
+            }
+            if (lane == 0) {
+                misc[M_ACTION] = action; misc[M_NF] = nf; misc[M_NE] = nE; misc[M_STOPKIND] = stop_kind;
+                misc[M_STATUS] = st_status; misc[M_PCOUNT] = 0; misc[M_ECOUNT] = 0;
+            }
+            if (lane < BL_R_POST) { pl_ts[lane] = ~0ull; pl_code[lane] = BL_CODE_END; }
+            __syncwarp();
+            a_rank[lane] = 0; a_flag[lane] = 0;
+        }
         __syncthreads();
-        if (tid == 0) { misc[M_PCOUNT] = 0; misc[M_ECOUNT] = 0; misc[M_OVERFLOW] = 0; }
-        if (overflow) {  // too many keys below theta: halve the window and post again (nothing has changed)
+        const int action = misc[M_ACTION];
+        int nf = misc[M_NF];
+        const int nE = misc[M_NE];
+        if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
+
+        if (action == ACT_OVERFLOW) {  // too many keys below theta: halve the window and post again
             win = bl_mul(win, 0.5);
             if (++shrinks >= 6) mode = MODE_ARGMIN;
-            if (prof_thread) { prof[7]++; prof[0] += clock64() - c0; }
+            if (prof_thread) prof[7]++;
             __syncthreads();
+            if (tid == 0) misc[M_ACTION] = ACT_BATCH;
             continue;
         }
         shrinks = 0;
-
-        // what this round turns out to be
-        int stop_kind = -1, st_status = BL_OK;  // stop_kind >= 0: leave the event loop with this bl_stop
-        int nf = 0;                              // collisions handed to resolve
-        bool repair = false;
-        const bool max_reached = P.max_events >= 0 && done >= P.max_events;
-        if (nE == 0) {
-            if (final_stage == 0 && !max_reached && mode == MODE_WINDOW && theta < end_excl) {
-                mode = MODE_ARGMIN;  // empty window: find the true minimum
-                win = bl_mul(win, 2.0);
-                if (prof_thread) { prof[7]++; prof[0] += clock64() - c0; }
-                __syncthreads();
-                continue;
-            }
-            stop_kind = max_reached ? BL_STOP_EVENTS : BL_STOP_TIME;  // nothing pending at or before end_time
-        } else {
-            // ---- sort by (ts, code, slot): rank by counting ----
-            for (int i = tid; i < nE; i += T) {
-                const uint64_t ts = e_ts[i], cd = e_code[i];
-                int r = 0;
-                for (int j = 0; j < nE; j++) {
-                    const uint64_t t2 = e_ts[j], c2 = e_code[j];
-                    r += (bl_key_less(t2, c2, ts, cd) || (t2 == ts && c2 == cd && j < i)) ? 1 : 0;
-                }
-                s_ts[r] = ts; s_code[r] = cd;
-            }
-            __syncthreads();
-            // ---- duplicates (adjacent), stale entries, ball conflicts with an earlier entry ----
-            for (int i = tid; i < nE; i += T) {
-                const uint64_t ts = s_ts[i], cd = s_code[i];
-                int f = 0;
-                if (cd == BL_CODE_STALE) f = F_STALE;
-                else if (i > 0 && s_ts[i - 1] == ts && s_code[i - 1] == cd) f = F_DUP;
-                else {
-                    int a, b;
-                    key_balls(cd, a, b);
-                    for (int j = 0; j < i; j++) {
-                        const uint64_t c2 = s_code[j];
-                        if (c2 == cd) continue;
-                        int a2, b2;
-                        key_balls(c2, a2, b2);
-                        if (a2 >= 0 && (a2 == a || a2 == b || (b2 >= 0 && (b2 == a || b2 == b)))) { f = F_CONFLICT; break; }
-                    }
-                }
-                s_flag[i] = f;
-                if (f & (F_STALE | F_CONFLICT)) atomicMin(&misc[M_CUT], i);
-            }
-            __syncthreads();
-            const int cut = misc[M_CUT] < nE ? misc[M_CUT] : nE;
-            const uint64_t ts0 = s_ts[0];
-            if (final_stage == 0 && max_reached) {
-                stop_kind = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
-            } else if (cut == 0) {
-                repair = true;  // the front entry is only a lower bound (it cannot be a conflict)
-            } else if (final_stage != 0) {
-                stop_kind = BL_STOP_TIME;  // query rounds only look at the front entry
-            } else if (ts0 == BL_TS_NAN) {
-                stop_kind = BL_STOP_ERROR; st_status = BL_ENAN;
-            } else if (ts0 >= end_excl) {
-                stop_kind = BL_STOP_TIME;
-            } else if (want_log && done >= P.log.cap) {
-                stop_kind = BL_STOP_LOG;
-            } else {
-                long long allowed = mode == MODE_ARGMIN ? 1 : m_max;
-                if (P.max_events >= 0 && P.max_events - done < allowed) allowed = P.max_events - done;
-                if (want_log && P.log.cap - done < allowed) allowed = P.log.cap - done;
-                // entries below the cut, duplicates skipped, in order
-                int r = 0;
-                for (int i = 0; i < cut && r < allowed; i++)
-                    if (!(s_flag[i] & F_DUP) && s_ts[i] < end_excl) r++;
-                nf = r;
-            }
+        if (action == ACT_EMPTY) {  // empty window: find the true minimum
+            mode = MODE_ARGMIN;
+            win = bl_mul(win, 2.0);
+            if (prof_thread) prof[7]++;
+            continue;
         }
-        __syncthreads();
-        if (tid == 0) misc[M_CUT] = BL_EV_CAP;
-        if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
 
         // =========================== repair: exact minima for the stale candidates near the front =============
         // The pairs of a stale ball k that matter are those written at a LATER collision of the other ball x
-        // (seq[x] >= seq[k]); their current values sit in row x, column k.  Every owner x reads its own row at the
+        // (seq[x] >= seq[k]); their current values sit in row x, column k.  Every ball x reads its own row at the
         // columns of all balls under repair (its rows: a handful of pages), the minima are reduced per CTA in
         // shared memory, across CTAs through global memory.
-        if (repair) {
+        if (action == ACT_REPAIR) {
             uint64_t hz = bl_sortable(bl_add(now, bl_mul(win, P.repair_horizon)));
             if (!(hz >= s_ts[0])) hz = s_ts[0];
-            const bool sel = own && mcode == BL_CODE_STALE && mts <= hz;
+            const bool sel = primary && own && c_mcode[bl] == BL_CODE_STALE && c_mts[bl] <= hz;
             int li = -1;
-            if (sel) { li = atomicAdd(&misc[M_NDIRTY], 1); dirty[li] = tid; }
+            if (sel) { li = atomicAdd(&misc[M_NDIRTY], 1); dirty[li] = bl; }
             __syncthreads();
             const int nd = misc[M_NDIRTY];
             if (tid == 0) misc[M_SBASE] = (ncta > 1 && nd) ? (int)atomicAdd(P.bar + 4, (unsigned)nd) : 0;
@@ -433,7 +561,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             const int sbase = misc[M_SBASE];
             if (sel) {
                 __stcg(P.stale_list + 2 * (size_t)(sbase + li), (uint64_t)k);
-                __stcg(P.stale_list + 2 * (size_t)(sbase + li) + 1, (uint64_t)myseq);
+                __stcg(P.stale_list + 2 * (size_t)(sbase + li) + 1, (uint64_t)c_seq[bl]);
             }
             sync_all(P, epoch);
             const int total = ncta > 1 ? (int)__ldcg(P.bar + 4) : nd;
@@ -441,6 +569,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             unsigned long long *smin_ts = reinterpret_cast<unsigned long long *>(sm + L.stash + BL_RCHUNK);
             int *q_k = reinterpret_cast<int *>(sm + L.stash + 2 * BL_RCHUNK);
             int *smin_x = q_k + BL_RCHUNK;
+            const long long myseq = c_seq[bl];
             int chunk = 0;
             for (int q0 = 0; q0 < total; q0 += BL_RCHUNK, chunk++) {
                 const int cn = total - q0 < BL_RCHUNK ? total - q0 : BL_RCHUNK;
@@ -450,17 +579,18 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     smin_ts[e] = ~0ull; smin_x[e] = 0x7fffffff;
                 }
                 __syncthreads();
-                for (int e0 = 0; e0 < cn; e0 += 16) {
-                    double v[16];
+                for (int g = 0; g < cn; g += 8 * H) {
+                    const int e0 = g + 8 * h;  // helper h takes the h-th group of eight
+                    double v[8];
 #pragma unroll
-                    for (int u = 0; u < 16; u++) {
+                    for (int u = 0; u < 8; u++) {
                         const int e = e0 + u;
                         const bool ok = own && e < cn && q_k[e] != k && myseq >= q_seq[e];
                         v[u] = ok ? __ldcg(myrow + q_k[e]) : BL_INF;
                     }
                     unsigned hit = 0;
 #pragma unroll
-                    for (int u = 0; u < 16; u++) {
+                    for (int u = 0; u < 8; u++) {
                         if (v[u] < BL_INF) {
                             const unsigned long long ts = bl_sortable(v[u]);
                             if (ts <= smin_ts[e0 + u]) { atomicMin(&smin_ts[e0 + u], ts); hit |= 1u << u; }
@@ -469,7 +599,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     __syncthreads();
                     // ties: the smallest pair code = the smallest partner index
 #pragma unroll
-                    for (int u = 0; u < 16; u++)
+                    for (int u = 0; u < 8; u++)
                         if ((hit >> u) & 1u)
                             if (bl_sortable(v[u]) == smin_ts[e0 + u]) atomicMin(&smin_x[e0 + u], k);
                 }
@@ -491,19 +621,19 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             if (bl_key_less(t2, x2, ts, xx)) { ts = t2; xx = x2; }
                         }
                         const int w = warp_argmin(ts, xx);
-                        ts = __shfl_sync(0xffffffffu, ts, w);
-                        xx = __shfl_sync(0xffffffffu, xx, w);
+                        ts = shfl_u64(ts, w);
+                        xx = shfl_u64(xx, w);
                     } else {
                         ts = smin_ts[e]; xx = (uint64_t)(unsigned)smin_x[e];
                     }
-                    if (lane == 0) { scratch[2 * dirty[d]] = ts; scratch[2 * dirty[d] + 1] = xx; }
+                    if (lane == 0) { scratch[3 * dirty[d]] = ts; scratch[3 * dirty[d] + 1] = xx; }
                 }
                 __syncthreads();
             }
             if (sel) {
-                const uint64_t ts = scratch[2 * tid];
-                if (ts == ~0ull) { mts = ts_inf; mcode = BL_CODE_NONE; }
-                else { mts = ts; mcode = bl_pair_code(k, (int)scratch[2 * tid + 1]); }
+                const uint64_t ts = scratch[3 * bl];
+                if (ts == ~0ull) { c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE; }
+                else { c_mts[bl] = ts; c_mcode[bl] = bl_pair_code(k, (int)scratch[3 * bl + 1]); }
             }
             if (tid == 0) { misc[M_NDIRTY] = 0; if (cta == 0 && ncta > 1) *(P.bar + 4) = 0; }
             if (prof_thread) { prof[3] += clock64() - c0; prof[4]++; n_rescans += nd; }
@@ -511,11 +641,28 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             continue;
         }
 
-        // =========================== stop / query stages ====================================================
-        if (stop_kind >= 0) {
+        // =========================== stop / query stages / error ==============================================
+        if (action == ACT_STOP || action == ACT_ERROR) {
             const bool writer = cta == 0 && tid == 0;
-            const uint64_t cd = nE > 0 ? s_code[0] : BL_CODE_END;
-            const double t = nE > 0 ? bl_unsortable(s_ts[0]) : BL_INF;
+            const uint64_t cd = s_code[0];
+            const double t = bl_unsortable(s_ts[0]);
+            if (action == ACT_ERROR) {
+                // rank 0 of the batch could not be resolved: the reference has moved to t and raised
+                if (writer) {
+                    res->err_i = bid[0]; res->err_j = bid[1];
+                    res->time = bt[0];
+                    res->stop = BL_STOP_ERROR; res->status = r_info[0];
+                    res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb;
+                    res->n_logged = want_log ? done : 0;
+                }
+                now = bt[0];
+                final_stage = 1; kindmask = KIND_BB; mode = MODE_ARGMIN;
+                __syncthreads();
+                if (primary) brank[bl] = -1;
+                __syncthreads();
+                continue;
+            }
+            const int stop_kind = misc[M_STOPKIND], st_status = misc[M_STATUS];
             if (final_stage == 0) {
                 if (writer) {
                     double tnow = now;
@@ -550,122 +697,98 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             break;
         }
-
-        // =========================== 3. resolve: one thread per collision of the batch ========================
-        // rank = position among the non-duplicate entries; the batch is the first nf of them
-        for (int i = tid; i < nE; i += T) {
-            if (s_flag[i] & F_DUP) continue;
-            int r = 0;
-            for (int j = 0; j < i; j++) r += (s_flag[j] & F_DUP) ? 0 : 1;
-            if (r >= nf) continue;
-            const uint64_t ts = s_ts[i], cd = s_code[i];
-            const double t = bl_unsortable(ts);
-            double *pl = r_pay + 13 * r;
-            int st = BL_OK;
-            if (cd & BL_CODE_OBS) {
-                // ---- ball-obstacle, simulation.py:504-519 + :604-636 ----
-                const int a = (int)(cd & 0x7fffffffull);
-                const double q0x = __ldcg(S.p0x + a), q0y = __ldcg(S.p0y + a), wvx = __ldcg(S.vx + a), wvy = __ldcg(S.vy + a);
-                const double wt0 = __ldcg(S.t0 + a), qarg = __ldcg(S.obs_arg + a);
-                const int oi = __ldcg(S.obs_idx + a);
-                const double ax = bl_advance(q0x, wvx, t, wt0), ay = bl_advance(q0y, wvy, t, wt0);
-                double nvx = wvx, nvy = wvy;
-                st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, wvx, wvy, qarg, nvx, nvy) : BL_EASSERT;
-                bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t;
-                bid[2 * r] = a; brc[2 * r] = S.rclass[a];
-                bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
-                pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
-                pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
-                r_info[4 * r] = st; r_info[4 * r + 1] = oi; r_info[4 * r + 2] = 0;
-                if (a >= base && a < base + T) brank[a - base] = r;
-            } else {
-                // ---- ball-ball, simulation.py:446-455 + :562-602 (a = idx1 < b = idx2) ----
-                const int a = bl_code_lo(cd), b = bl_code_hi(cd);
-                const double a0x = __ldcg(S.p0x + a), a0y = __ldcg(S.p0y + a), a_vx = __ldcg(S.vx + a), a_vy = __ldcg(S.vy + a);
-                const double a_t0 = __ldcg(S.t0 + a);
-                const double b0x = __ldcg(S.p0x + b), b0y = __ldcg(S.p0y + b), b_vx = __ldcg(S.vx + b), b_vy = __ldcg(S.vy + b);
-                const double b_t0 = __ldcg(S.t0 + b);
-                double m1 = S.mass[a], m2 = S.mass[b];
-                const double ax = bl_advance(a0x, a_vx, t, a_t0), ay = bl_advance(a0y, a_vy, t, a_t0);
-                const double bxx = bl_advance(b0x, b_vx, t, b_t0), byy = bl_advance(b0y, b_vy, t, b_t0);
-                bl_remap_masses(m1, m2);
-                double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
-                st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
-                bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t;
-                bid[2 * r] = a; brc[2 * r] = S.rclass[a];
-                bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
-                bid[2 * r + 1] = b; brc[2 * r + 1] = S.rclass[b];
-                pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
-                pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
-                r_info[4 * r] = st; r_info[4 * r + 1] = -1; r_info[4 * r + 2] = 1;
-                if (a >= base && a < base + T) brank[a - base] = r;
-                if (b >= base && b < base + T) brank[b - base] = r;
-            }
-            if (st != BL_OK) atomicMin(&misc[M_ERRRANK], r);
-        }
-        __syncthreads();
-        const int er = misc[M_ERRRANK];
-        __syncthreads();
-        if (er < nf) {
-            // the collision at this rank cannot be resolved (physics.py:277-279 / zero masses): commit what comes
-            // before it; if it is the front one, stop here with the reference's error
-            if (tid == 0) misc[M_ERRRANK] = BL_EV_CAP;
-            if (er == 0) {
-                if (cta == 0 && tid == 0) {
-                    res->err_i = bid[0]; res->err_j = bid[1];
-                    res->time = bt[0];  // the reference has moved to t
-                    res->stop = BL_STOP_ERROR; res->status = r_info[0];
-                    res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb;
-                    res->n_logged = want_log ? done : 0;
-                }
-                now = bt[0];
-                final_stage = 1; kindmask = KIND_BB; mode = MODE_ARGMIN;
-                __syncthreads();
-                brank[tid] = -1;
-                __syncthreads();
-                continue;
-            }
-            nf = er;
-        }
         if (prof_thread) { const long long c2 = clock64(); prof[1] += c2 - c0; c0 = c2; }
 
-        // =========================== 4. solve: my pair with every ball of the batch ===========================
-        int myrank = brank[tid];
+        // =========================== 4. solve: my ball against the balls of the batch =========================
+        // helper h takes the collisions r = h, h + H, ...
+        int myrank = brank[bl];
         if (myrank >= nf) myrank = -1;
         const uint64_t vbound = bl_sortable(bt[2 * (nf - 1)]);  // time of the last collision of the batch
         uint64_t vmin = ~0ull;
+        const double p0x = st_p0x[bl], p0y = st_p0y[bl], vx = st_vx[bl], vy = st_vy[bl], t0 = st_t0[bl];
         double nx = 0, ny = 0, nvx = 0, nvy = 0, nt0 = 0;   // my state after my own collision (batch balls only)
-        uint64_t n_ots = 0;
-        if (own) {
-            if (myrank >= 0) {
-                const int myj = bid[2 * myrank] == k ? 2 * myrank : 2 * myrank + 1;
-                nx = bx[myj]; ny = by[myj]; nvx = bvx[myj]; nvy = bvy[myj]; nt0 = bt[myj];
+        if (own && myrank >= 0) {
+            const int myj = bid[2 * myrank] == k ? 2 * myrank : 2 * myrank + 1;
+            nx = bx[myj]; ny = by[myj]; nvx = bvx[myj]; nvy = bvy[myj]; nt0 = bt[myj];
+            if (h == H - 1) {
                 // my next obstacle after the collision, simulation.py:490-495 / :545-547
                 double ot, oarg;
                 int oi;
-                bl_next_obstacle<FMA>(obs, n_obs, S.rsum2_obs, K, myrc, nx, ny, nvx, nvy, c_radius[tid], nt0, ot, oi, oarg);
-                n_ots = bl_sortable(ot);
-                scratch[2 * tid] = as_u(oarg); scratch[2 * tid + 1] = (uint64_t)(unsigned)oi;
+                bl_next_obstacle<FMA>(obs, n_obs, S.rsum2_obs, K, myrc, nx, ny, nvx, nvy, c_radius[bl], nt0, ot, oi, oarg);
+                const uint64_t n_ots = bl_sortable(ot);
+                scratch[3 * bl] = n_ots; scratch[3 * bl + 1] = as_u(oarg); scratch[3 * bl + 2] = (uint64_t)(unsigned)oi;
                 if (n_ots <= vbound && myrank < nf - 1) vmin = n_ots;
             }
-            const int nb = 2 * nf;
-            for (int j = 0; j < nb; j++) {
-                const int x = bid[j];
-                const int r = j >> 1;
-                if (x < 0 || r == myrank) continue;  // no ball, me, or my partner in the same collision
-                const double t = bt[j];
-                // my state as of just before that collision
-                const bool after = myrank >= 0 && myrank < r;
-                const double sx = after ? nx : p0x, sy = after ? ny : p0y, svx = after ? nvx : vx, svy = after ? nvy : vy;
-                const double st0 = after ? nt0 : t0;
-                const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
-                const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
-                const double v = bl_add(t, bl_toi_ball_ball<FMA>(bx[j], by[j], bvx[j], bvy[j], px, py, svx, svy, rs));
-                stash[(size_t)j * T + tid] = v;
-                const uint64_t vs = bl_sortable(v);
-                if (vs <= vbound && r < nf - 1) vmin = vs < vmin ? vs : vmin;
+        }
+        // Pass 1, branch-free: advance my ball to the collision time once, then form the quadratic of
+        // physics.py:33-54 against both balls of the collision.  Only ~5 % of the pairs get past the two early
+        // exits; those are queued per warp and finished densely (sqrt + division) by all 32 lanes.
+        {
+            double *const q_b = wq + warp * (4 * BL_WQ_CAP), *const q_c = q_b + BL_WQ_CAP, *const q_d = q_c + BL_WQ_CAP;
+            int *const q_dst = reinterpret_cast<int *>(q_d + BL_WQ_CAP);
+            int qn = 0;
+            for (int r = h;; r += H) {
+                unsigned m0 = 0, m1 = 0;
+                bool hit0 = false, hit1 = false;
+                double b0 = 0, c0q = 0, d0 = 0, b1 = 0, c1q = 0, d1 = 0;
+                const bool last = r >= nf;
+                if (!last) {
+                    const double t = bt[2 * r];
+                    const bool valid = own && r != myrank;  // not me / my partner in the same collision
+                    // my state as of just before that collision
+                    const bool after = myrank >= 0 && myrank < r;
+                    const double sx = after ? nx : p0x, sy = after ? ny : p0y, svx = after ? nvx : vx, svy = after ? nvy : vy;
+                    const double st0 = after ? nt0 : t0;
+                    const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
+                    const int x1 = bid[2 * r + 1];
+                    {
+                        const int j = 2 * r;
+                        const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
+                        const double dpx = bl_sub(px, bx[j]), dpy = bl_sub(py, by[j]);
+                        const double dvx = bl_sub(svx, bvx[j]), dvy = bl_sub(svy, bvy[j]);
+                        b0 = bl_dot2<FMA>(dpx, dpy, dvx, dvy);
+                        c0q = bl_sub(bl_dot2<FMA>(dpx, dpy, dpx, dpy), rs);
+                        d0 = bl_sub(bl_mul(b0, b0), bl_mul(bl_dot2<FMA>(dvx, dvy, dvx, dvy), c0q));
+                        hit0 = valid && !(b0 >= 0.0) && !(d0 <= 0.0);
+                        if (valid) stash[(size_t)j * Tb + bl] = BL_INF;
+                    }
+                    if (x1 >= 0) {
+                        const int j = 2 * r + 1;
+                        const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
+                        const double dpx = bl_sub(px, bx[j]), dpy = bl_sub(py, by[j]);
+                        const double dvx = bl_sub(svx, bvx[j]), dvy = bl_sub(svy, bvy[j]);
+                        b1 = bl_dot2<FMA>(dpx, dpy, dvx, dvy);
+                        c1q = bl_sub(bl_dot2<FMA>(dpx, dpy, dpx, dpy), rs);
+                        d1 = bl_sub(bl_mul(b1, b1), bl_mul(bl_dot2<FMA>(dvx, dvy, dvx, dvy), c1q));
+                        hit1 = valid && !(b1 >= 0.0) && !(d1 <= 0.0);
+                        if (valid) stash[(size_t)j * Tb + bl] = BL_INF;
+                    }
+                    m0 = __ballot_sync(0xffffffffu, hit0);
+                    m1 = __ballot_sync(0xffffffffu, hit1);
+                }
+                const int cnt = __popc(m0) + __popc(m1);
+                if (last || qn + cnt > BL_WQ_CAP) {
+                    // Pass 2, dense: t1 = c / (-b + sqrt(disc)); entry = time + (t1 if t1 >= t_eps else inf)
+                    __syncwarp();
+                    for (int i = lane; i < qn; i += 32) {
+                        const int dst = q_dst[i], j = dst >> 16;
+                        const double t1 = bl_div(q_c[i], bl_add(-q_b[i], bl_sqrt(q_d[i])));
+                        const double v = bl_add(bt[j], t1 >= BL_T_EPS ? t1 : BL_INF);
+                        stash[(size_t)j * Tb + (dst & 0xffff)] = v;
+                        const uint64_t vs = bl_sortable(v);
+                        if (vs <= vbound && (j >> 1) < nf - 1) vmin = vs < vmin ? vs : vmin;
+                    }
+                    __syncwarp();
+                    qn = 0;
+                }
+                if (last) break;
+                if (hit0) { const int i = qn + __popc(m0 & lt_mask); q_b[i] = b0; q_c[i] = c0q; q_d[i] = d0; q_dst[i] = ((2 * r) << 16) | bl; }
+                qn += __popc(m0);
+                if (hit1) { const int i = qn + __popc(m1 & lt_mask); q_b[i] = b1; q_c[i] = c1q; q_d[i] = d1; q_dst[i] = ((2 * r + 1) << 16) | bl; }
+                qn += __popc(m1);
             }
         }
+        if (prof_thread) { const long long cs = clock64(); prof[10] += cs - c0; c0 = cs; }
         if (nf > 1) {
             const uint64_t wmin = warp_min_u64(vmin);
             if (lane == 0 && wmin != ~0ull) atomicMin(m_viol, (unsigned long long)wmin);
@@ -673,12 +796,12 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             if (ncta > 1) {
                 if (tid == 0) __stcg(P.viol + (size_t)par * BL_MAX_CTAS + cta, (uint64_t)*m_viol);
                 sync_all(P, epoch);
-                uint64_t h = ~0ull;
+                uint64_t hh = ~0ull;
                 for (int c = lane; c < ncta; c += 32) {
                     const uint64_t v2 = __ldcg(P.viol + (size_t)par * BL_MAX_CTAS + c);
-                    h = v2 < h ? v2 : h;
+                    hh = v2 < hh ? v2 : hh;
                 }
-                vmin = warp_min_u64(h);
+                vmin = warp_min_u64(hh);
             } else {
                 vmin = (uint64_t)*m_viol;
             }
@@ -686,6 +809,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             if (tid == 0) *m_viol = ~0ull;
         } else {
             vmin = ~0ull;
+            __syncthreads();  // the parked values of a ball come from all of its helpers' warps
         }
         // collisions committed: the first one always, the others while they come before every violation
         int nc = 1;
@@ -693,54 +817,75 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         if (prof_thread) { const long long c3 = clock64(); prof[2] += c3 - c0; c0 = c3; }
 
         // =========================== 5. commit ===============================================================
-        if (own) {
-            const bool mine = myrank >= 0 && myrank < nc;  // my own collision is committed
-            // the new values I am responsible for, folded into one candidate
-            uint64_t c_ts = ts_inf, c_code = BL_CODE_NONE;
-            bool partner_hit = false;
-            int q = -1;
-            if (!mine && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
-            const int nb = 2 * nc;
-            for (int j = 0; j < nb; j++) {
-                const int x = bid[j];
-                const int r = j >> 1;
-                if (x < 0) continue;
-                if (r == myrank) {
-                    // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
-                    if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
-                    continue;
-                }
-                if (mine && r < myrank) continue;  // that pair is re-solved at my (later) collision by x's owner
-                // my cell in the row of the ball whose collision is the later one of the pair
-                const double v = stash[(size_t)j * T + tid];
-                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
-                if (x == q) partner_hit = true;
-                if (v < BL_INF) {
-                    const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
-                    if (bl_key_less(vs, vc, c_ts, c_code)) { c_ts = vs; c_code = vc; }
+        const bool mine = myrank >= 0 && myrank < nc;  // my ball's own collision is committed
+        {
+            // helper h stores and folds the new values of the collisions r = h, h + H, ...
+            uint64_t f_ts = ts_inf, f_code = BL_CODE_NONE;
+            int f_hit = 0;
+            if (own) {
+                int q = -1;
+                const uint64_t mcode = c_mcode[bl];
+                if (!mine && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
+                for (int r = h; r < nc; r += H) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int j = 2 * r + u;
+                        const int x = bid[j];
+                        if (x < 0) continue;
+                        if (r == myrank) {
+                            // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
+                            if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
+                            continue;
+                        }
+                        if (mine && r < myrank) continue;  // that pair is re-solved at my (later) collision, from x's side
+                        // my cell in the row of the ball whose collision is the later one of the pair
+                        const double v = stash[(size_t)j * Tb + bl];
+                        __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
+                        if (x == q) f_hit = 1;
+                        if (v < BL_INF) {
+                            const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
+                            if (bl_key_less(vs, vc, f_ts, f_code)) { f_ts = vs; f_code = vc; }
+                        }
+                    }
                 }
             }
-            if (mine) {
-                // my cover is emptied and refilled with the pairs solved at later collisions of the batch
-                mts = c_code != BL_CODE_NONE ? c_ts : ts_inf; mcode = c_code;
-                p0x = nx; p0y = ny; vx = nvx; vy = nvy; t0 = nt0;
-                ots = n_ots;
-                c_oarg[tid] = as_d(scratch[2 * tid]);
-                c_oidx[tid] = (int)scratch[2 * tid + 1];
-                // keep the global mirror current: resolvers read ball states from it
-                __stcg(S.p0x + k, p0x); __stcg(S.p0y + k, p0y); __stcg(S.vx + k, vx); __stcg(S.vy + k, vy);
-                __stcg(S.t0 + k, t0);
-                __stcg(S.obs_arg + k, c_oarg[tid]); __stcg(S.obs_idx + k, c_oidx[tid]);
-                myseq = seq_base + done + myrank + 1;
-                __stcg(S.seq + k, myseq);
-            } else if (mcode == BL_CODE_STALE) {
-                if (c_code != BL_CODE_NONE && c_ts < mts) { mts = c_ts; mcode = c_code; }  // strictly earlier: decisive
-            } else if (partner_hit) {
-                // the entry that was my candidate has just been overwritten
-                if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { mts = c_ts; mcode = c_code; }
-                else mcode = BL_CODE_STALE;  // the old time stays as a lower bound
-            } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
-                mts = c_ts; mcode = c_code;
+            if (H > 1) {
+                fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit;
+                __syncthreads();
+            }
+            if (primary && own) {
+                uint64_t c_ts = f_ts, c_code = f_code;
+                bool partner_hit = f_hit != 0;
+                for (int g = 1; g < H; g++) {
+                    const uint64_t t2 = fold[2 * (g * Tb + bl)], c2 = fold[2 * (g * Tb + bl) + 1];
+                    if (bl_key_less(t2, c2, c_ts, c_code)) { c_ts = t2; c_code = c2; }
+                    partner_hit = partner_hit || fold_hit[g * Tb + bl] != 0;
+                }
+                const uint64_t mts = c_mts[bl], mcode = c_mcode[bl];
+                if (mine) {
+                    // my cover is emptied and refilled with the pairs solved at later collisions of the batch
+                    c_mts[bl] = c_code != BL_CODE_NONE ? c_ts : ts_inf; c_mcode[bl] = c_code;
+                    st_p0x[bl] = nx; st_p0y[bl] = ny; st_vx[bl] = nvx; st_vy[bl] = nvy; st_t0[bl] = nt0;
+                    c_ots[bl] = scratch[3 * bl];
+                    const double oarg = as_d(scratch[3 * bl + 1]);
+                    const int oi = (int)scratch[3 * bl + 2];
+                    c_oarg[bl] = oarg; c_oidx[bl] = oi;
+                    const long long sq = seq_base + done + myrank + 1;
+                    c_seq[bl] = sq;
+                    // keep the global mirror current: resolvers read ball states from it
+                    __stcg(S.p0x + k, nx); __stcg(S.p0y + k, ny); __stcg(S.vx + k, nvx); __stcg(S.vy + k, nvy);
+                    __stcg(S.t0 + k, nt0);
+                    __stcg(S.obs_arg + k, oarg); __stcg(S.obs_idx + k, oi);
+                    __stcg(S.seq + k, sq);
+                } else if (mcode == BL_CODE_STALE) {
+                    if (c_code != BL_CODE_NONE && c_ts < mts) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }  // strictly earlier: decisive
+                } else if (partner_hit) {
+                    // the entry that was my candidate has just been overwritten
+                    if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }
+                    else c_mcode[bl] = BL_CODE_STALE;  // the old time stays as a lower bound
+                } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
+                    c_mts[bl] = c_ts; c_mcode[bl] = c_code;
+                }
             }
         }
         // event log, simulation.py:590-594 / :626-631 payloads
@@ -776,22 +921,23 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             else if (nE > P.target + (P.target >> 1)) win = bl_mul(win, 0.75);
         }
         __syncthreads();
-        brank[tid] = -1;
+        if (primary) brank[bl] = -1;
         if (prof_thread) prof[6] += clock64() - c0;
         // the next barrier (post) orders this round's global stores before anybody reads them
     }
 
     // ---- write back the resident cache ------------------------------------------------------------------
-    if (own) {
-        S.cover_t[k] = bl_unsortable(mts); S.cover_code[k] = mcode;
-        S.obs_t[k] = bl_unsortable(ots);
-        S.obs_idx[k] = c_oidx[tid];
-        S.obs_arg[k] = c_oarg[tid];
+    __syncthreads();
+    if (primary && own) {
+        S.cover_t[k] = bl_unsortable(c_mts[bl]); S.cover_code[k] = c_mcode[bl];
+        S.obs_t[k] = bl_unsortable(c_ots[bl]);
+        S.obs_idx[k] = c_oidx[bl];
+        S.obs_arg[k] = c_oarg[bl];
     }
     if (tid == 0 && n_rescans) atomicAdd((unsigned long long *)&res->n_rescans, (unsigned long long)n_rescans);
     if (cta == 0 && tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) res->prof[q] = prof[q];
+        for (int q = 0; q < 16; q++) res->prof[q] = prof[q];
         res->window = win;
         *S.seq_counter = seq_base + done;
     }
@@ -801,11 +947,12 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// CTA shape: one ball per thread.  Up to 2048 balls run as one cluster of <= 16 small CTAs (hardware barrier);
-// larger systems use one CTA of >= 128 threads per SM and a cooperative launch.
-int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode) {
-    if (n <= 0) { *ncta = 1; *threads = 32; *sync_mode = SYNC_CTA; return BL_OK; }
-    if (n <= 64) { *ncta = 1; *threads = ((n + 31) / 32) * 32; *sync_mode = SYNC_CTA; return BL_OK; }
+// CTA shape: Tb balls per CTA, H threads per ball.  Up to 2048 balls run as one cluster of <= 16 CTAs (hardware
+// barrier); larger systems use one CTA of >= 128 balls per SM and a cooperative launch.
+static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, int *sync_mode) {
+    *hh = 1;
+    if (n <= 0) { *ncta = 1; *tb = 32; *sync_mode = SYNC_CTA; return BL_OK; }
+    if (n <= 64) { *ncta = 1; *tb = ((n + 31) / 32) * 32; *hh = n > 8 ? 4 : 1; *sync_mode = SYNC_CTA; return BL_OK; }
     if (n <= 2048) {
         int c = (n + 127) / 128;
         if (c < 2) c = 2;
@@ -814,19 +961,27 @@ int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, in
         c = p;
         int t = (n + c - 1) / c;
         t = ((t + 31) / 32) * 32;
-        *ncta = c; *threads = t; *sync_mode = SYNC_CLUSTER;
+        *ncta = c; *tb = t; *hh = 4; *sync_mode = SYNC_CLUSTER;
         return BL_OK;
     }
     int t = 128;
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
     while ((n + t - 1) / t > sms && t <= BL_MAX_THREADS) t += 32;
     if (t > BL_MAX_THREADS) return BL_EUNSUPPORTED;
-    *ncta = (n + t - 1) / t; *threads = t; *sync_mode = SYNC_GRID;
+    *ncta = (n + t - 1) / t; *tb = t; *sync_mode = SYNC_GRID;
+    *hh = t <= 128 ? 4 : (t <= 256 ? 2 : 1);
     return BL_OK;
 }
 
-static int pick_m_max(int threads) {
-    int m = (BL_STASH_BYTES / 16) / threads;  // 2 values of 8 bytes per collision and thread
+int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode) {
+    int tb, hh;
+    const int rc = pick_shape(h, n, ncta, &tb, &hh, sync_mode);
+    *threads = tb * hh;
+    return rc;
+}
+
+static int pick_m_max(int tb) {
+    int m = (BL_STASH_BYTES / 16) / tb;  // 2 values of 8 bytes per collision and ball
     if (m > BL_M_MAX) m = BL_M_MAX;
     if (m < 1) m = 1;
     return m;
@@ -837,9 +992,10 @@ static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
     auto kern = bl_evolve_kernel<FMA, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaFuncSetAttribute(smem)");
+    const unsigned threads = (unsigned)(P.Tb * P.H);
     if (P.sync_mode == SYNC_GRID) {
         void *args[1] = {(void *)&P};
-        e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)P.ncta), dim3((unsigned)P.T), args, smem, st);
+        e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)P.ncta), dim3(threads), args, smem, st);
         return bl_check_cuda(h, e, "cooperative launch of bl_evolve_kernel");
     }
     if (P.ncta > 8) {
@@ -848,7 +1004,7 @@ static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)P.ncta, 1, 1);
-    cfg.blockDim = dim3((unsigned)P.T, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -864,19 +1020,20 @@ static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
 
 int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st) {
-    int ncta, threads, sync_mode;
-    int rc = bl_evolve_pick_config(h, s->n, &ncta, &threads, &sync_mode);
+    int ncta, tb, hh, sync_mode;
+    int rc = pick_shape(h, s->n, &ncta, &tb, &hh, &sync_mode);
     if (rc != BL_OK)
         return bl_set_error(h, rc, "the event kernel keeps ball state resident on chip: n=%d exceeds %d CTAs x %d "
-                            "threads", s->n, h->sm_count, BL_MAX_THREADS);
+                            "balls", s->n, h->sm_count, BL_MAX_THREADS);
     Params P;
     P.s = *s;
     P.time = time; P.end_time = end_time; P.max_events = max_events; P.first_kind = first_kind;
     P.query_only = query_only;
     if (log) P.log = *log; else { P.log.cap = 0; P.log.t = nullptr; P.log.i = nullptr; P.log.j = nullptr; P.log.payload = nullptr; }
     P.result = h->d_result;
-    P.T = threads; P.ncta = ncta; P.sync_mode = sync_mode;
-    P.m_max = pick_m_max(threads);
+    P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
+    P.m_max = pick_m_max(tb);
+    if (P.m_max > 32) P.m_max = 32;  // the sorted batch lives in the lanes of one warp
     // collisions per round the window aims at: the chance that a round is cut short grows like 2 m^2 / n
     int target = 1;
     while ((long long)(target + 1) * (target + 1) * 20 <= (long long)s->n) target++;
@@ -889,7 +1046,7 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.bar = h->d_bar; P.post = h->d_post; P.viol = h->d_viol;
     P.stale_list = h->d_stale; P.partial = h->d_partial;
     P.repair_horizon = h->repair_horizon;
-    size_t smem = (size_t)make_layout(P.T, P.m_max, s->n_obstacles).words * 8;
+    size_t smem = (size_t)make_layout(P.Tb, P.H, P.m_max, s->n_obstacles).words * 8;
     if (smem > h->max_smem_optin)
         return bl_set_error(h, BL_EUNSUPPORTED, "event kernel needs %zu B of shared memory per CTA (limit %zu)", smem,
                             h->max_smem_optin);
@@ -898,7 +1055,7 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     e = cudaMemsetAsync(h->d_bar, 0, 64, st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset barrier");
     h->launches++;
-    if (threads <= 256)
-        return h->dot_fma ? launch_t<true, 256>(h, P, smem, st) : launch_t<false, 256>(h, P, smem, st);
+    if (tb * hh <= 512)
+        return h->dot_fma ? launch_t<true, 512>(h, P, smem, st) : launch_t<false, 512>(h, P, smem, st);
     return h->dot_fma ? launch_t<true, BL_MAX_THREADS>(h, P, smem, st) : launch_t<false, BL_MAX_THREADS>(h, P, smem, st);
 }

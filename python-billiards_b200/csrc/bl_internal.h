@@ -36,6 +36,7 @@ struct bl_handle {
 #define BL_R_POST 6           // keys one CTA may post per round
 #define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
 #define BL_M_MAX 48           // collisions committed per round, at most
+#define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
 #define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
 

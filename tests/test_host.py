@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     from billiards import _lib
     assert ctypes.sizeof(_lib.BlObstacle) == 40
     assert ctypes.sizeof(_lib.BlSystem) == 16 + 19 * 8
-    assert ctypes.sizeof(_lib.BlResult) == 8 * 10 + 8 + 8 * 4 + 64 + 8
+    assert ctypes.sizeof(_lib.BlResult) == 8 * 10 + 8 + 8 * 4 + 128 + 8
     assert ctypes.sizeof(_lib.BlLog) == 40
 
 
