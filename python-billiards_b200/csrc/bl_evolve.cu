@@ -89,8 +89,8 @@ struct Layout {
     int bx, by, bvx, bvy, bt;         // [2*m_max] batch balls: state right after their collision
     int bid, brc;                     // [2*m_max] ints: ball index (-1: none), radius class
     int e_ts, e_code;                 // [BL_EV_CAP] collected keys (unsorted)
-    int s_ts, s_code;                 // [32] sorted keys
-    int s_flag, a_rank, a_flag;       // [32] ints: flags in sorted order; rank and flags by collection slot
+    int s_ts, s_code;                 // [BL_SORT_CAP] sorted keys
+    int s_flag, a_rank, a_flag;       // [BL_SORT_CAP] ints: flags in sorted order; rank and flags by collection slot
     int r_pay;                        // [m_max][13] log payload per rank
     int r_info;                       // [m_max][4] ints: status, obstacle index, is ball-ball, pad
     int pl_ts, pl_code;               // [BL_R_POST] this CTA's posted keys
@@ -116,8 +116,8 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.bt = w; w += 2 * m_max;
     L.bid = w; w += m_max; L.brc = w; w += m_max;
     L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP;
-    L.s_ts = w; w += 32; L.s_code = w; w += 32;
-    L.s_flag = w; w += 16; L.a_rank = w; w += 16; L.a_flag = w; w += 16;
+    L.s_ts = w; w += BL_SORT_CAP; L.s_code = w; w += BL_SORT_CAP;
+    L.s_flag = w; w += BL_SORT_CAP / 2; L.a_rank = w; w += BL_SORT_CAP / 2; L.a_flag = w; w += BL_SORT_CAP / 2;
     L.r_pay = w; w += 13 * m_max;
     L.r_info = w; w += 2 * m_max;
     L.pl_ts = w; w += BL_R_POST; L.pl_code = w; w += BL_R_POST;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double *const myrow = S.toi + (size_t)(own ? k : 0) * (size_t)S.pitch;
     if (tid < 32) sm[L.misc + tid] = 0;
     if (tid < BL_R_POST) { pl_ts[tid] = ~0ull; pl_code[tid] = BL_CODE_END; }
-    if (tid < 32) { a_rank[tid] = 0; a_flag[tid] = 0; }
+    if (tid < BL_SORT_CAP) { a_rank[tid] = 0; a_flag[tid] = 0; }
     __syncthreads();
     if (tid == 0) *m_viol = ~0ull;
     const int myrc = c_rclass[bl];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // rank[i]++; and if they share a ball, i is a duplicate (same pair, posted by both balls) or a conflict
         {
             const int nr = misc[M_ECOUNT];
-            if (mode == MODE_WINDOW && nr > 1 && nr <= 32) {
+            if (mode == MODE_WINDOW && nr > 1 && nr <= BL_SORT_CAP) {
                 for (int p = tid; p < nr * nr; p += T) {
                     const int i = p / nr, j = p - i * nr;
                     const uint64_t ti = e_ts[i], ci = e_code[i], tj = e_ts[j], cj = e_code[j];
@@ -403,18 +403,28 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             int nE = misc[M_ECOUNT];
             int action = misc[M_ACTION] == ACT_OVERFLOW ? ACT_OVERFLOW : ACT_BATCH;
             int stop_kind = 0, st_status = BL_OK, nf = 0;
-            uint64_t ts = ~0ull, cd = BL_CODE_END;
+            // sorted entries `lane` and `lane + 32`
+            uint64_t ts0 = ~0ull, cd0 = BL_CODE_END, ts1 = ~0ull, cd1 = BL_CODE_END;
+            int fl0 = 0, fl1 = 0;
             if (mode == MODE_ARGMIN) {
                 // only the smallest of the per-CTA minima is known to be next
                 for (int i = lane; i < nE && i < BL_EV_CAP; i += 32)
-                    if (bl_key_less(e_ts[i], e_code[i], ts, cd)) { ts = e_ts[i]; cd = e_code[i]; }
-                const int w = warp_argmin(ts, cd);
-                ts = shfl_u64(ts, w); cd = shfl_u64(cd, w);
-                if (lane != 0) { ts = ~0ull; cd = BL_CODE_END; }
+                    if (bl_key_less(e_ts[i], e_code[i], ts0, cd0)) { ts0 = e_ts[i]; cd0 = e_code[i]; }
+                const int w = warp_argmin(ts0, cd0);
+                ts0 = shfl_u64(ts0, w); cd0 = shfl_u64(cd0, w);
+                if (lane != 0) { ts0 = ~0ull; cd0 = BL_CODE_END; }
                 nE = nE > 0 ? 1 : 0;
-            } else {
-                if (nE > 32) action = ACT_OVERFLOW;
-                else if (lane < nE) { ts = e_ts[lane]; cd = e_code[lane]; }
+            } else if (nE > BL_SORT_CAP) {
+                action = ACT_OVERFLOW;
+            } else if (nE == 1) {
+                if (lane == 0) { ts0 = e_ts[0]; cd0 = e_code[0]; }
+            } else if (nE > 1) {
+                // into sorted order (ranks and flags come from the pair pass)
+                if (lane < nE) { const int rk = a_rank[lane]; s_ts[rk] = e_ts[lane]; s_code[rk] = e_code[lane]; s_flag[rk] = a_flag[lane]; }
+                if (lane + 32 < nE) { const int rk = a_rank[lane + 32]; s_ts[rk] = e_ts[lane + 32]; s_code[rk] = e_code[lane + 32]; s_flag[rk] = a_flag[lane + 32]; }
+                __syncwarp();
+                if (lane < nE) { ts0 = s_ts[lane]; cd0 = s_code[lane]; fl0 = s_flag[lane]; }
+                if (lane + 32 < nE) { ts1 = s_ts[lane + 32]; cd1 = s_code[lane + 32]; fl1 = s_flag[lane + 32]; }
             }
             const bool max_reached = P.max_events >= 0 && done >= P.max_events;
             if (action == ACT_OVERFLOW) {
@@ -423,30 +433,21 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 else { action = ACT_STOP; stop_kind = max_reached ? BL_STOP_EVENTS : BL_STOP_TIME; }
                 if (lane == 0) { s_ts[0] = ts_inf; s_code[0] = BL_CODE_END; }
             } else {
-                // ---- into sorted order (ranks and flags come from the pair pass) ----
-                int fl = 0;
-                if (nE > 1) {
-                    if (lane < nE) { const int rk = a_rank[lane]; s_ts[rk] = ts; s_code[rk] = cd; s_flag[rk] = a_flag[lane]; }
-                    __syncwarp();
-                    if (lane < nE) { ts = s_ts[lane]; cd = s_code[lane]; fl = s_flag[lane]; }
-                }
-                int a, b;
-                key_balls(cd, a, b);
-                const bool stale = lane < nE && cd == BL_CODE_STALE;
-                const bool dup = (fl & F_DUP) != 0, conflict = (fl & F_CONFLICT) != 0;
                 if (prof_thread) prof[14] += clock64() - c0;
-                const unsigned cutmask = __ballot_sync(0xffffffffu, lane < nE && (stale || conflict));
-                const int cut = cutmask ? __ffs(cutmask) - 1 : nE;
-                const uint64_t ts0 = shfl_u64(ts, 0);
+                // the batch ends before the first entry that is only a lower bound or shares a ball with an earlier one
+                const unsigned cm0 = __ballot_sync(0xffffffffu, lane < nE && (cd0 == BL_CODE_STALE || (fl0 & F_CONFLICT)));
+                const unsigned cm1 = __ballot_sync(0xffffffffu, lane + 32 < nE && (cd1 == BL_CODE_STALE || (fl1 & F_CONFLICT)));
+                const int cut = cm0 ? __ffs(cm0) - 1 : (cm1 ? 31 + __ffs(cm1) : nE);
+                const uint64_t tsf = shfl_u64(ts0, 0);
                 if (final_stage == 0 && max_reached) {
                     action = ACT_STOP; stop_kind = BL_STOP_EVENTS;  // checked first: the clock stays at the last collision
                 } else if (cut == 0) {
                     action = ACT_REPAIR;  // the front entry is only a lower bound (it cannot be a conflict)
                 } else if (final_stage != 0) {
                     action = ACT_STOP; stop_kind = BL_STOP_TIME;  // query rounds only look at the front entry
-                } else if (ts0 == BL_TS_NAN) {
+                } else if (tsf == BL_TS_NAN) {
                     action = ACT_STOP; stop_kind = BL_STOP_ERROR; st_status = BL_ENAN;
-                } else if (ts0 >= end_excl) {
+                } else if (tsf >= end_excl) {
                     action = ACT_STOP; stop_kind = BL_STOP_TIME;
                 } else if (want_log && done >= P.log.cap) {
                     action = ACT_STOP; stop_kind = BL_STOP_LOG;
@@ -454,14 +455,23 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     long long allowed = mode == MODE_ARGMIN ? 1 : m_max;
                     if (P.max_events >= 0 && P.max_events - done < allowed) allowed = P.max_events - done;
                     if (want_log && P.log.cap - done < allowed) allowed = P.log.cap - done;
-                    const bool valid = lane < cut && !dup && ts < end_excl;
-                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-                    const int r = __popc(vm & lt_mask);
-                    nf = __popc(vm);
+                    const bool valid0 = lane < cut && !(fl0 & F_DUP) && ts0 < end_excl;
+                    const bool valid1 = lane + 32 < cut && !(fl1 & F_DUP) && ts1 < end_excl;
+                    const unsigned vm0 = __ballot_sync(0xffffffffu, valid0), vm1 = __ballot_sync(0xffffffffu, valid1);
+                    const int r0 = __popc(vm0 & lt_mask), r1 = __popc(vm0) + __popc(vm1 & lt_mask);
+                    nf = __popc(vm0) + __popc(vm1);
                     if (nf > allowed) nf = (int)allowed;
                     // ---- resolve: one lane per collision of the batch (rank r) ----
-                    int st = BL_OK;
-                    if (valid && r < nf) {
+                    int er_mine = 0x7fffffff;
+                    const int halves = nf > __popc(vm0) ? 2 : 1;
+#pragma unroll 1
+                    for (int hf = 0; hf < halves; hf++) {
+                        const uint64_t ts = hf ? ts1 : ts0, cd = hf ? cd1 : cd0;
+                        const int r = hf ? r1 : r0;
+                        if (!((hf ? valid1 : valid0) && r < nf)) continue;
+                        int a, b;
+                        key_balls(cd, a, b);
+                        int st = BL_OK;
                         const double t = bl_unsortable(ts);
                         double *pl = r_pay + 13 * r;
                         if (cd & BL_CODE_OBS) {
@@ -503,15 +513,16 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             if (a >= base && a < base + Tb) brank[a - base] = r;
                             if (b >= base && b < base + Tb) brank[b - base] = r;
                         }
+                        if (st != BL_OK && r < er_mine) er_mine = r;
                     }
                     if (prof_thread) prof[15] += clock64() - c0;
                     // a collision that cannot be resolved (physics.py:277-279 / zero masses): commit what comes
                     // before it; if it is the front one, stop with the reference's error
-                    const int er = __reduce_min_sync(0xffffffffu, (valid && r < nf && st != BL_OK) ? r : 0x7fffffff);
+                    const int er = __reduce_min_sync(0xffffffffu, er_mine);
                     if (er < nf) nf = er;
                     if (nf == 0) action = ACT_ERROR;
                 }
-                if (lane == 0) { s_ts[0] = ts; s_code[0] = cd; }  // the front entry, for the stop stages
+                if (lane == 0) { s_ts[0] = ts0; s_code[0] = cd0; }  // the front entry, for the stop stages
             }
             if (lane == 0) {
                 misc[M_ACTION] = action; misc[M_NF] = nf; misc[M_NE] = nE; misc[M_STOPKIND] = stop_kind;
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             if (lane < BL_R_POST) { pl_ts[lane] = ~0ull; pl_code[lane] = BL_CODE_END; }
             __syncwarp();
-            a_rank[lane] = 0; a_flag[lane] = 0;
+            a_rank[lane] = 0; a_flag[lane] = 0; a_rank[lane + 32] = 0; a_flag[lane + 32] = 0;
         }
         __syncthreads();
         const int action = misc[M_ACTION];
@@ -1033,7 +1044,6 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.result = h->d_result;
     P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
     P.m_max = pick_m_max(tb);
-    if (P.m_max > 32) P.m_max = 32;  // the sorted batch lives in the lanes of one warp
     // collisions per round the window aims at: the chance that a round is cut short grows like 2 m^2 / n
     int target = 1;
     while ((long long)(target + 1) * (target + 1) * 20 <= (long long)s->n) target++;

@@ -35,6 +35,7 @@ struct bl_handle {
 #define BL_POST_WORDS 16      // header + BL_R_POST keys of 2 words
 #define BL_R_POST 6           // keys one CTA may post per round
 #define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
+#define BL_SORT_CAP 64        // keys a window round sorts (two per lane of warp 0); more -> the window is halved
 #define BL_M_MAX 48           // collisions committed per round, at most
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
 #define BL_RCHUNK 256         // stale candidates repaired per pass

@@ -17,6 +17,8 @@ from billiards import _lib  # noqa: E402
 
 fma = _lib.probe_dot_fma()
 h = _lib.get_handle(0, fma)
+if os.environ.get("BL_TARGET"):
+    h.check(h.lib.bl_set_batch_target(h.h, int(os.environ["BL_TARGET"])))
 NAMES = ("post+collect+sort", "resolve", "solve+violation", "repair")
 
 
