@@ -42,6 +42,9 @@ import workloads  # noqa: E402
 INF = float("inf")
 FP64_FLOPS_PER_SINAI_COLLISION = 60.0   # algorithmic adds/muls/divs/sqrts per collision (fma = 2)
 SM_COUNT, FP64_LANES_PER_SM = 148, 64
+# FP64 FMA peak measured on this pool's B200 with tools/microbench.cu (profiles/r1_microbench.log): 37.13 TFLOP/s,
+# 64.0 FMA/clk/SM -- the datasheet formula at the observed clock; used when MEASURED_PEAKS.json has no FP64 entry
+MEASURED_FP64_TFLOPS = 37.13
 
 
 def load_peaks():
@@ -153,7 +156,7 @@ def bench_gas(args, device, fma):
     n_bb = n_bo = 0
     kernel_ms = 0.0
     rescans = 0
-    prof = [0] * 8
+    prof = [0] * 16
     barrier(device)
     ev0.record()
     for _ in range(args.steps):
@@ -178,7 +181,8 @@ def bench_gas(args, device, fma):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1),
                 "kernel_ms_per_launch": kernel_ms / max(args.steps, 1),
-                "note": "event chain is serial: latency-bound by design, see DESIGN.md"}
+                "note": "one launch commits batches of causally independent collisions per grid-wide round; the "
+                        "rounds are bound by synchronisation + FP64 latency, not by HBM (DESIGN.md section 5)"}
 
     # e2e: host arrays -> Billiard -> E collisions -> host arrays, every step
     e2e_steps = max(1, min(args.steps, 5))
@@ -220,11 +224,13 @@ def bench_gas(args, device, fma):
         "config": {"workload": f"dense_gas_{N}", "balls": N, "packing_fraction": 0.5, "obstacles": "4 InfiniteWall",
                    "collisions_per_step": E, "table_bytes": int(N) * ((N + 15) // 16 * 16) * 8,
                    "l2": "inputs larger than L2 (table 2.1 GB, one event touches 4 rows/columns of it)",
-                   "cluster": list(_evolve_config(h, N)), "dot_fma": bool(fma)},
+                   "ctas_x_threads": list(_evolve_config(h, N)), "dot_fma": bool(fma)},
         "counts": {"ball_ball": n_bb, "ball_obstacle": n_bo, "stale_row_rescans": rescans},
-        "phase_cycles_per_event": {k: prof[q] / max(n_bb + n_bo, 1) for q, k in
-                                   enumerate(("argmin_and_barrier", "resolve", "solve_and_update", "stale_row_repair"))},
-        "repair_phases": prof[4], "loop_iterations": prof[5],
+        "phase_cycles_per_round": {k: prof[q] / max(prof[5], 1) for k, q in
+                                   (("post", 8), ("barrier_1", 9), ("collect_analyse_resolve", 0), ("solve", 10),
+                                    ("violation_exchange_barrier_2", 2), ("commit", 6), ("repair", 3))},
+        "repair_phases": prof[4], "rounds": prof[5], "reposted_rounds": prof[7],
+        "collisions_per_round": (n_bb + n_bo) / max(prof[5], 1),
         "build_seconds": build_s,
     }, cfg
 
@@ -274,12 +280,12 @@ def bench_ensemble(args, device, fma, rank, world, steps, warmup):
     local_done = int(ens.stats()[0].item()) - before
     done_all = local_done * world  # every rank runs the same number of collisions per system
     value = done_all / (total_ms * 1e-3)
-    _, _, sm_max = load_peaks()
-    fp64_peak = SM_COUNT * FP64_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12   # TFLOP/s counting fma = 2
+    fp64_peak = MEASURED_FP64_TFLOPS   # TFLOP/s counting fma = 2
     achieved = local_done * FP64_FLOPS_PER_SINAI_COLLISION / (kernel_ms * 1e-3) / 1e12
     roofline = {"kernel": "bl_ensemble_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
-                "peak_source": "148 SM x 64 FP64 lanes x 2 x sm_max_mhz (datasheet formula; no measured FP64 peak)",
+                "peak_source": "measured DFMA peak, tools/microbench.cu (profiles/r1_microbench.log); equals "
+                               "148 SM x 64 lanes x 2 x 1.96 GHz",
                 "algorithmic_flops_per_collision": FP64_FLOPS_PER_SINAI_COLLISION,
                 "kernel_ms_per_launch": kernel_ms / max(steps, 1)}
     # e2e: host arrays in, host results out, every step
@@ -425,8 +431,8 @@ def main():
         gas, _ = bench_gas(args, device, fma)
         line.update({k: gas[k] for k in ("value", "ms_per_step", "config", "roofline", "e2e", "clocks", "gpu_launches")})
         line["counts"] = gas["counts"]
-        line["phase_cycles_per_event"] = gas["phase_cycles_per_event"]
-        line["repair_phases"] = gas["repair_phases"]
+        for key in ("phase_cycles_per_round", "repair_phases", "rounds", "reposted_rounds", "collisions_per_round"):
+            line[key] = gas[key]
         line["table_build_seconds"] = gas["build_seconds"]
         ens_steps = max(1, min(args.steps, 3))
         ens = bench_ensemble(args, device, fma, rank, world, ens_steps, 1)

@@ -1044,10 +1044,11 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.result = h->d_result;
     P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
     P.m_max = pick_m_max(tb);
-    // collisions per round the window aims at: the chance that a round is cut short grows like 2 m^2 / n
+    // collisions per round the window aims at: the chance that a round is cut short by a violation grows like
+    // m^2 / n, the synchronisation cost per collision falls like 1 / m (measured optimum ~ sqrt(n / 8))
     int target = 1;
-    while ((long long)(target + 1) * (target + 1) * 20 <= (long long)s->n) target++;
-    if (target > (2 * P.m_max) / 3) target = (2 * P.m_max) / 3;
+    while ((long long)(target + 1) * (target + 1) * 8 <= (long long)s->n) target++;
+    if (target > P.m_max - 4) target = P.m_max - 4;
     if (target < 1) target = 1;
     if (h->target_override > 0) target = h->target_override < P.m_max ? h->target_override : P.m_max;
     P.target = target;
