@@ -137,6 +137,92 @@ def test_against_oracle_seeded(billiards, oracle, n_side, n_events):
     assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
 
 
+def _oracle_log(oracle, cfg, fma, n_events):
+    ref = cfg.build_oracle(oracle, dot_fma=fma, flags=oracle.FAST_ROWMIN)
+    ref.enable_log(n_events)
+    ref.evolve(INF, max_events=n_events)
+    return ref, ref.log()
+
+
+@pytest.mark.parametrize("n_side,n_events", [(48, 4000), (128, 6000)])
+def test_grid_mode_long_run_against_oracle(billiards, oracle, n_side, n_events):
+    """More than 2048 balls: cooperative grid launch, global-memory barrier, windows of dozens of collisions per
+    round, several stale-candidate repair phases -- event by event against the CPU oracle."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.dense_gas(n_side)
+    ref, (rt, ri, rj) = _oracle_log(oracle, cfg, fma, n_events)
+    bld = build(billiards, cfg, fma)
+    _, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+    assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+    assert_bits_equal(t, rt, "event times")
+    assert bld.last_result.prof[5] < n_events / 4, "rounds should commit several collisions each"
+    st = ref.state()
+    assert_bits_equal(bld.balls_velocity, st["v"])
+    assert_bits_equal(bld.balls_initial_position, st["p0"])
+    assert_bits_equal(bld.balls_initial_time[:, 0], st["t0"])
+    bt, bi, ot, oo, _ = ref.minima()
+    assert_bits_equal(bld._balls_toi, bt)          # goes through bl_symmetrize
+    assert [int(x) for x in bld._balls_idx] == bi.tolist()
+    assert_bits_equal(bld._obstacles_toi, ot)
+    if n_side <= 48:
+        assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
+
+
+@pytest.mark.parametrize("target", [1, 2, 5, 17, 44])
+def test_batch_size_does_not_change_results(billiards, oracle, target):
+    """Collisions per synchronisation round is a speed knob only: same log, same table, same state for every value."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    for cfg, n_events in ((workloads.hetero_gas(), 3000), (workloads.dense_gas(34, seed=7, phi=0.45), 2500),
+                          (workloads.dense_gas(47, seed=3), 2500)):
+        ref, (rt, ri, rj) = _oracle_log(oracle, cfg, fma, n_events)
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            _, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+        assert_bits_equal(t, rt, "event times")
+        assert_bits_equal(bld.balls_velocity, ref.state()["v"])
+        assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
+
+
+def test_stops_inside_a_batch(billiards, oracle):
+    """Count-based and time-based stops that fall in the middle of a window: many short launches == one launch."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.dense_gas(47, seed=11)
+    n_events = 3000
+    ref, (rt, ri, rj) = _oracle_log(oracle, cfg, fma, n_events)
+    bld = build(billiards, cfg, fma)
+    ts, is_, js = [], [], []
+    chunks = [1, 2, 3, 5, 7, 11, 13, 64, 1, 100, 257]
+    done = 0
+    while done < n_events:
+        k = min(chunks[len(ts) % len(chunks)], n_events - done)
+        c, (t, i, j) = bld.evolve_events(k, log_capacity=k)
+        assert sum(c) == k
+        ts.append(t); is_.append(i); js.append(j)
+        done += k
+    assert np.concatenate(is_).tolist() == ri.tolist() and np.concatenate(js).tolist() == rj.tolist()
+    assert_bits_equal(np.concatenate(ts), rt, "event times")
+    assert_bits_equal(bld.balls_velocity, ref.state()["v"])
+    # time-based: frames of a fixed dt, as visualize_matplotlib.animate drives evolve
+    a, b = build(billiards, cfg, fma), build(billiards, cfg, fma)
+    t_end = float(rt[1500])
+    total = (0, 0)
+    for f in range(1, 201):
+        c = a.evolve(t_end * f / 200)
+        total = (total[0] + c[0], total[1] + c[1])
+    assert total == b.evolve(t_end)
+    assert_bits_equal(a.balls_position, b.balls_position)
+    assert_bits_equal(a.balls_velocity, b.balls_velocity)
+    assert_bits_equal(np.concatenate(a.toi_table), np.concatenate(b.toi_table), "toi_table")
+
+
 def test_stop_resume_is_bit_stable(billiards, oracle):
     """tests/test_simulation.py:461-502: 300 partial evolves == one evolve, exactly; and == the oracle."""
     from billiards import _lib
