@@ -60,6 +60,8 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
     {
         const char *hz = getenv("BL_REPAIR_HORIZON");
         h->repair_horizon = hz ? atof(hz) : 8.0;
+        const char *eg = getenv("BL_ENSEMBLE_GENERIC");
+        h->ensemble_generic = eg ? atoi(eg) : 0;
     }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");

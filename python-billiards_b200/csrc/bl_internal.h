@@ -27,6 +27,7 @@ struct bl_handle {
     int window_n;
     const void *window_sys;
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
+    int ensemble_generic;     // BL_ENSEMBLE_GENERIC=1: always use the generic (list in shared memory) ensemble kernel
     char err[512];
 };
 
