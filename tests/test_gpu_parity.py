@@ -317,6 +317,51 @@ def test_sinai_ensemble(billiards, golden, oracle):
     assert one.time == want["t"][7]
 
 
+def test_ensemble_kernel_variants(billiards, oracle):
+    """Obstacle lists that take the generic kernel (disk first, two disks, nine walls), a radius > 0, and more than
+    65535 collisions per launch (the packed per-obstacle hit counters are flushed in between)."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    walls = workloads.box_walls(-1, -1, 1, 1)
+    lists = {
+        "disk_first": [("disk", (0.0, 0.0), 0.5)] + walls,
+        "two_disks": walls + [("disk", (-0.4, 0.1), 0.2), ("disk", (0.45, -0.3), 0.25)],
+        "walls_only": walls,
+        "octagon": walls + [("wall", (1.3, 0.0), (0.0, 1.3), "left"), ("wall", (0.0, 1.3), (-1.3, 0.0), "left"),
+                            ("wall", (-1.3, 0.0), (0.0, -1.3), "left"), ("wall", (0.0, -1.3), (1.3, 0.0), "left"),
+                            ("disk", (0.0, 0.0), 0.3)],
+    }
+    rng = np.random.default_rng(11)
+    for name, obstacles in lists.items():
+        n = 3000
+        pos = rng.uniform(-0.95, 0.95, (n, 2))
+        ok = np.ones(n, dtype=bool)
+        for ob in obstacles:
+            if ob[0] == "disk":
+                ok &= ((pos - np.asarray(ob[1])) ** 2).sum(axis=1) > (ob[2] + 0.03) ** 2
+        pos = pos[ok]
+        theta = rng.uniform(0, 2 * np.pi, len(pos))
+        vel = np.stack([np.cos(theta), np.sin(theta)], axis=1)
+        radius = 0.0 if name != "two_disks" else 0.02
+        ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, radius=radius,
+                                         dot_fma=fma, count_hits=True)
+        ens.run(500)
+        want = oracle.ensemble_run(workloads.oracle_obstacles(obstacles), pos, vel, 500, radius=radius, dot_fma=fma,
+                                   count_hits=True)
+        assert_bits_equal(ens.time, want["t"], name)
+        assert_bits_equal(ens.balls_velocity, want["v"], name)
+        assert_bits_equal(ens.balls_initial_position, want["p0"], name)
+        assert ens.hits.tolist() == want["hits"].tolist(), name
+    obstacles, pos, vel = workloads.sinai(96, seed=2)
+    ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, dot_fma=fma, count_hits=True)
+    ens.run(70000)
+    want = oracle.ensemble_run(workloads.oracle_obstacles(obstacles), pos, vel, 70000, dot_fma=fma, count_hits=True)
+    assert_bits_equal(ens.time, want["t"])
+    assert_bits_equal(ens.balls_velocity, want["v"])
+    assert ens.hits.tolist() == want["hits"].tolist()
+    assert int(ens.hits.sum()) == 96 * 70000
+
+
 def test_unit_vectors(billiards, golden):
     from billiards import physics
     g = golden("unit_vectors")
