@@ -99,7 +99,8 @@ struct Layout {
     int mts, mcode, ots;              // [Tb] candidate key, next-obstacle time (sortable)
     int seq;                          // [Tb] sequence number of the ball's last collision
     int mass, radius, oarg;           // [Tb] doubles
-    int oidx, brank, rclass;          // [Tb] ints
+    int oidx, brank, rclass;          // [Tb] ints (brank: [2][Tb])
+    int undo;                         // [11][Tb] state before the optimistic commit of the last batch
     int dirty;                        // [Tb] ints
     int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
     int fold;                         // [H][Tb][2] partial candidate of each helper + [H][Tb] ints partner-hit
@@ -112,21 +113,23 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     Layout L;
     int w = 0;
     L.stash = w; w += 2 * m_max * Tb;
-    L.bx = w; w += 2 * m_max; L.by = w; w += 2 * m_max; L.bvx = w; w += 2 * m_max; L.bvy = w; w += 2 * m_max;
-    L.bt = w; w += 2 * m_max;
-    L.bid = w; w += m_max; L.brc = w; w += m_max;
+    // batch tables: two copies, the previous round's batch is finalised while the next one is being resolved
+    L.bx = w; w += 4 * m_max; L.by = w; w += 4 * m_max; L.bvx = w; w += 4 * m_max; L.bvy = w; w += 4 * m_max;
+    L.bt = w; w += 4 * m_max;
+    L.bid = w; w += 2 * m_max; L.brc = w; w += 2 * m_max;
     L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP;
     L.s_ts = w; w += BL_SORT_CAP; L.s_code = w; w += BL_SORT_CAP;
     L.s_flag = w; w += BL_SORT_CAP / 2; L.a_rank = w; w += BL_SORT_CAP / 2; L.a_flag = w; w += BL_SORT_CAP / 2;
-    L.r_pay = w; w += 13 * m_max;
-    L.r_info = w; w += 2 * m_max;
+    L.r_pay = w; w += 2 * 13 * m_max;
+    L.r_info = w; w += 2 * 2 * m_max;
     L.pl_ts = w; w += BL_R_POST; L.pl_code = w; w += BL_R_POST;
     L.w_ts = w; w += 32; L.w_code = w; w += 32;
     L.p0x = w; w += Tb; L.p0y = w; w += Tb; L.vx = w; w += Tb; L.vy = w; w += Tb; L.t0 = w; w += Tb;
     L.mts = w; w += Tb; L.mcode = w; w += Tb; L.ots = w; w += Tb;
     L.seq = w; w += Tb;
     L.mass = w; w += Tb; L.radius = w; w += Tb; L.oarg = w; w += Tb;
-    L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += (Tb + 1) / 2; L.rclass = w; w += (Tb + 1) / 2;
+    L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += Tb; L.rclass = w; w += (Tb + 1) / 2;
+    L.undo = w; w += 11 * Tb;
     L.dirty = w; w += (Tb + 1) / 2;
     L.scratch = w; w += 3 * Tb;
     L.fold = w; w += H * Tb * 2 + (H * Tb + 1) / 2;
@@ -138,7 +141,7 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
 }
 // ints of `misc`; M_VIOL is a 64-bit word index
 enum { M_PCOUNT = 0, M_ECOUNT, M_NDIRTY, M_SBASE, M_ACTION, M_NF, M_NE, M_STOPKIND, M_STATUS };
-enum { M_VIOL = 8 };
+enum { M_VIOL = 8, M_GMIN = 9 };
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -216,15 +219,15 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     const int cta = blockIdx.x, ncta = P.ncta, m_max = P.m_max;
     const Layout L = make_layout(Tb, H, m_max, n_obs);
     double *stash = reinterpret_cast<double *>(sm + L.stash);
-    double *bx = reinterpret_cast<double *>(sm + L.bx), *by = reinterpret_cast<double *>(sm + L.by);
-    double *bvx = reinterpret_cast<double *>(sm + L.bvx), *bvy = reinterpret_cast<double *>(sm + L.bvy);
-    double *bt = reinterpret_cast<double *>(sm + L.bt);
-    int *bid = reinterpret_cast<int *>(sm + L.bid), *brc = reinterpret_cast<int *>(sm + L.brc);
+    double *const bx_b = reinterpret_cast<double *>(sm + L.bx), *const by_b = reinterpret_cast<double *>(sm + L.by);
+    double *const bvx_b = reinterpret_cast<double *>(sm + L.bvx), *const bvy_b = reinterpret_cast<double *>(sm + L.bvy);
+    double *const bt_b = reinterpret_cast<double *>(sm + L.bt);
+    int *const bid_b = reinterpret_cast<int *>(sm + L.bid), *const brc_b = reinterpret_cast<int *>(sm + L.brc);
     uint64_t *e_ts = sm + L.e_ts, *e_code = sm + L.e_code, *s_ts = sm + L.s_ts, *s_code = sm + L.s_code;
     int *s_flag = reinterpret_cast<int *>(sm + L.s_flag), *a_rank = reinterpret_cast<int *>(sm + L.a_rank);
     int *a_flag = reinterpret_cast<int *>(sm + L.a_flag);
-    double *r_pay = reinterpret_cast<double *>(sm + L.r_pay);
-    int *r_info = reinterpret_cast<int *>(sm + L.r_info);
+    double *const r_pay_b = reinterpret_cast<double *>(sm + L.r_pay);
+    int *const r_info_b = reinterpret_cast<int *>(sm + L.r_info);
     uint64_t *pl_ts = sm + L.pl_ts, *pl_code = sm + L.pl_code, *w_ts = sm + L.w_ts, *w_code = sm + L.w_code;
     double *st_p0x = reinterpret_cast<double *>(sm + L.p0x), *st_p0y = reinterpret_cast<double *>(sm + L.p0y);
     double *st_vx = reinterpret_cast<double *>(sm + L.vx), *st_vy = reinterpret_cast<double *>(sm + L.vy);
@@ -233,7 +236,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     long long *c_seq = reinterpret_cast<long long *>(sm + L.seq);
     double *c_mass = reinterpret_cast<double *>(sm + L.mass), *c_radius = reinterpret_cast<double *>(sm + L.radius);
     double *c_oarg = reinterpret_cast<double *>(sm + L.oarg);
-    int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *brank = reinterpret_cast<int *>(sm + L.brank);
+    int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *const brank_b = reinterpret_cast<int *>(sm + L.brank);
+    uint64_t *const undo = sm + L.undo;  // [f][Tb], f = 0 mts, 1 mcode, 2..6 p0x p0y vx vy t0, 7 ots, 8 oarg, 9 oidx, 10 seq
     int *c_rclass = reinterpret_cast<int *>(sm + L.rclass);
     int *dirty = reinterpret_cast<int *>(sm + L.dirty);
     uint64_t *scratch = sm + L.scratch;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     const bl_obstacle *obs = reinterpret_cast<const bl_obstacle *>(sm + L.obs);
     int *misc = reinterpret_cast<int *>(sm + L.misc);
     unsigned long long *m_viol = reinterpret_cast<unsigned long long *>(sm + L.misc + M_VIOL);
+    unsigned long long *m_gmin = reinterpret_cast<unsigned long long *>(sm + L.misc + M_GMIN);
 
     const int base = cta * Tb;
     const int k = base + bl;  // the ball this thread serves
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             c_seq[bl] = 0; c_rclass[bl] = 0; c_mass[bl] = 0; c_radius[bl] = 0; c_oarg[bl] = 0; c_oidx[bl] = -1;
             c_ots[bl] = ts_inf; c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE;
         }
-        brank[bl] = -1;
+        brank_b[bl] = -1; brank_b[Tb + bl] = -1;
     }
     const double rs11 = (K == 1 && n > 0) ? S.rsum2[0] : 0.0;
     double *const myrow = S.toi + (size_t)(own ? k : 0) * (size_t)S.pitch;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     if (tid < BL_R_POST) { pl_ts[tid] = ~0ull; pl_code[tid] = BL_CODE_END; }
     if (tid < BL_SORT_CAP) { a_rank[tid] = 0; a_flag[tid] = 0; }
     __syncthreads();
-    if (tid == 0) *m_viol = ~0ull;
+    if (tid == 0) { *m_viol = ~0ull; *m_gmin = ~0ull; }
     const int myrc = c_rclass[bl];
 
     const bool prof_thread = warp == 0;  // the whole warp reads the clock: a single-lane branch would leave warp 0 diverged
@@ -301,15 +306,132 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     __syncthreads();
     if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 
+    // ---- the two halves of a commit; shared by the optimistic commit, the deferred row stores and the redo ----
+    // helper half: the collisions r = h, h + H, ... < nc_ of a batch (ball list Bbid): store my cells of the
+    // colliding balls' rows and / or fold my new values into one candidate
+    auto helper_pass = [&](const int *Bbid, const int nc_, const int myrank_, const bool mine_, const bool stores,
+                           const bool folds, uint64_t &f_ts, uint64_t &f_code, int &f_hit) {
+        f_ts = ts_inf; f_code = BL_CODE_NONE; f_hit = 0;
+        if (!own) return;
+        int q = -1;
+        if (folds) {
+            const uint64_t mcode = c_mcode[bl];
+            if (!mine_ && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
+        }
+        for (int r = h; r < nc_; r += H) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int j = 2 * r + u;
+                const int x = Bbid[j];
+                if (x < 0) continue;
+                if (r == myrank_) {
+                    // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
+                    if (stores && x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
+                    continue;
+                }
+                if (mine_ && r < myrank_) continue;  // that pair is re-solved at my (later) collision, from x's side
+                // my cell in the row of the ball whose collision is the later one of the pair
+                const double v = stash[(size_t)j * Tb + bl];
+                if (stores) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
+                if (folds) {
+                    if (x == q) f_hit = 1;
+                    if (v < BL_INF) {
+                        const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
+                        if (bl_key_less(vs, vc, f_ts, f_code)) { f_ts = vs; f_code = vc; }
+                    }
+                }
+            }
+        }
+    };
+    // primary half: combine the helpers' partial candidates and update the ball
+    auto primary_apply = [&](const double *Bx, const double *By, const double *Bvx, const double *Bvy, const double *Bt,
+                             const int *Bbid, const int myrank_, const bool mine_, uint64_t c_ts, uint64_t c_code,
+                             bool partner_hit, const long long done_base, const bool save_undo) {
+        for (int g = 1; g < H; g++) {
+            const uint64_t t2 = fold[2 * (g * Tb + bl)], c2 = fold[2 * (g * Tb + bl) + 1];
+            if (bl_key_less(t2, c2, c_ts, c_code)) { c_ts = t2; c_code = c2; }
+            partner_hit = partner_hit || fold_hit[g * Tb + bl] != 0;
+        }
+        const uint64_t mts = c_mts[bl], mcode = c_mcode[bl];
+        if (save_undo) { undo[bl] = mts; undo[Tb + bl] = mcode; }
+        if (mine_) {
+            if (save_undo) {
+                undo[2 * Tb + bl] = as_u(st_p0x[bl]); undo[3 * Tb + bl] = as_u(st_p0y[bl]); undo[4 * Tb + bl] = as_u(st_vx[bl]);
+                undo[5 * Tb + bl] = as_u(st_vy[bl]); undo[6 * Tb + bl] = as_u(st_t0[bl]); undo[7 * Tb + bl] = c_ots[bl];
+                undo[8 * Tb + bl] = as_u(c_oarg[bl]); undo[9 * Tb + bl] = (uint64_t)(unsigned)c_oidx[bl];
+                undo[10 * Tb + bl] = (uint64_t)c_seq[bl];
+            }
+            const int myj = Bbid[2 * myrank_] == k ? 2 * myrank_ : 2 * myrank_ + 1;
+            const double nx = Bx[myj], ny = By[myj], nvx = Bvx[myj], nvy = Bvy[myj], nt0 = Bt[myj];
+            // my cover is emptied and refilled with the pairs solved at later collisions of the batch
+            c_mts[bl] = c_code != BL_CODE_NONE ? c_ts : ts_inf; c_mcode[bl] = c_code;
+            st_p0x[bl] = nx; st_p0y[bl] = ny; st_vx[bl] = nvx; st_vy[bl] = nvy; st_t0[bl] = nt0;
+            c_ots[bl] = scratch[3 * bl];
+            const double oarg = as_d(scratch[3 * bl + 1]);
+            const int oi = (int)scratch[3 * bl + 2];
+            c_oarg[bl] = oarg; c_oidx[bl] = oi;
+            const long long sq = seq_base + done_base + myrank_ + 1;
+            c_seq[bl] = sq;
+            // keep the global mirror current: resolvers read ball states from it
+            __stcg(S.p0x + k, nx); __stcg(S.p0y + k, ny); __stcg(S.vx + k, nvx); __stcg(S.vy + k, nvy);
+            __stcg(S.t0 + k, nt0);
+            __stcg(S.obs_arg + k, oarg); __stcg(S.obs_idx + k, oi);
+            __stcg(S.seq + k, sq);
+        } else if (mcode == BL_CODE_STALE) {
+            if (c_code != BL_CODE_NONE && c_ts < mts) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }  // strictly earlier: decisive
+        } else if (partner_hit) {
+            // the entry that was my candidate has just been overwritten
+            if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }
+            else c_mcode[bl] = BL_CODE_STALE;  // the old time stays as a lower bound
+        } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
+            c_mts[bl] = c_ts; c_mcode[bl] = c_code;
+        }
+    };
+    // clock, counters and window after nc_ of the nf_ collisions of a batch have been committed
+    auto advance_clock = [&](const double *Bt, const int *Br_info, const int nc_, const int nf_, const int nE_) {
+        for (int r = 0; r < nc_; r++) n_bb += Br_info[4 * r + 2];
+        done += nc_;
+        prev_now = now;
+        now = Bt[2 * (nc_ - 1)];
+        if (mode == MODE_ARGMIN) {
+            kindmask = KIND_BOTH;  // only the first event's kind was forced
+            if (!(win > 0.0)) {
+                const double gap = bl_sub(now, prev_now);
+                if (done >= 2 && gap > 0.0) win = bl_mul(gap, (double)P.target);
+            }
+            if (win > 0.0) mode = MODE_WINDOW;
+        } else {
+            if (nc_ < nf_) win = bl_mul(win, 0.5);
+            else if (2 * nE_ < P.target) win = bl_mul(win, 1.5);
+            else if (nE_ > P.target + (P.target >> 1)) win = bl_mul(win, 0.75);
+        }
+    };
+    // the last batch: committed optimistically, validated (and its rows stored) one barrier later
+    bool pending = false;
+    int nf_prev = 0, pb = 0, u_nE = 0, u_mode = mode, u_kind = kindmask;
+    long long u_done = 0, u_nbb = 0;
+    double u_now = now, u_prev_now = now, u_win = win;
+
     for (;;) {
         long long c0 = 0;
         if (prof_thread) { c0 = clock64(); prof[5]++; }
+        // batch tables of this round, and of the previous batch
+        double *const bx = bx_b + pb * 2 * m_max, *const by = by_b + pb * 2 * m_max, *const bvx = bvx_b + pb * 2 * m_max;
+        double *const bvy = bvy_b + pb * 2 * m_max, *const bt = bt_b + pb * 2 * m_max;
+        int *const bid = bid_b + pb * 2 * m_max, *const brc = brc_b + pb * 2 * m_max;
+        double *const r_pay = r_pay_b + pb * 13 * m_max;
+        int *const r_info = r_info_b + pb * 4 * m_max, *const brank = brank_b + pb * Tb;
+        const int qb = pb ^ 1;
+        const double *const pbt = bt_b + qb * 2 * m_max;
+        const int *const pbid = bid_b + qb * 2 * m_max;
+        int *const pbrank = brank_b + qb * Tb;
         // =========================== 1. post =================================================================
         uint64_t theta = 0;
         if (mode == MODE_WINDOW) {
             theta = bl_sortable(bl_add(now, win));
             if (theta > end_excl) theta = end_excl;
         }
+        if (tid == 0) *m_gmin = ~0ull;
         if (warp < (Tb >> 5)) {  // the primaries' warps
             uint64_t kts = ~0ull, kcode = BL_CODE_END;
             if (own) {
@@ -346,10 +468,13 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             if (tid == 0) word = pack2(pc < BL_R_POST ? pc : BL_R_POST, pc > BL_R_POST ? 1 : 0);
             else word = (tid & 1) ? pl_ts[(tid - 1) >> 1] : pl_code[(tid - 1) >> 1];
             __stcg(post + (tid ? tid + 1 : 0), word);  // header in word 0, key e in words 2+2e, 3+2e (16-byte aligned)
+            // word 1: the earliest violating new key of the batch this CTA has just committed optimistically
+            if (tid == 0) __stcg(post + 1, pending ? (uint64_t)*m_viol : ~0ull);
         }
         long long cb = 0;
         if (prof_thread) cb = clock64();
         sync_all(P, epoch);
+        if (tid == 0) *m_viol = ~0ull;
         if (prof_thread) { const long long ce = clock64(); prof[8] += cb - c0; prof[9] += ce - cb; c0 = ce; }
         // =========================== 2. collect ==============================================================
         {
@@ -357,11 +482,12 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             for (int c = tid; c < ncta; c += T) {
                 const uint64_t *rec = box + (size_t)c * BL_POST_WORDS;
                 // one trip: header and the first two keys (a CTA rarely posts more)
-                const uint64_t hd = __ldcg(rec);
+                const uint64_t hd = __ldcg(rec), vw = __ldcg(rec + 1);
                 const ulonglong2 k0 = __ldcg(reinterpret_cast<const ulonglong2 *>(rec + 2));
                 const ulonglong2 k1 = __ldcg(reinterpret_cast<const ulonglong2 *>(rec + 4));
                 const int cnt = lo32(hd);
                 if (hi32(hd)) misc[M_ACTION] = ACT_OVERFLOW;
+                if (vw != ~0ull) atomicMin(m_gmin, (unsigned long long)vw);
                 if (cnt > 0) {
                     const int slot = atomicAdd(&misc[M_ECOUNT], cnt);
                     if (slot < BL_EV_CAP) { e_ts[slot] = k0.x; e_code[slot] = k0.y; }
@@ -374,6 +500,79 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         par ^= 1;
         __syncthreads();
         if (prof_thread) prof[11] += clock64() - c0;
+
+        // =========================== 2b. validate the previous batch ===========================================
+        // It was committed optimistically (candidates, states, mirrors) before this round's keys were posted; its
+        // violation minimum came with the keys.  Normally nothing violates: only the row stores and the log are
+        // left to do.  Otherwise the commit is rolled back and redone for the valid prefix, and the keys -- posted
+        // from a state that never existed -- are thrown away.
+        if (pending) {
+            const uint64_t gmin = (uint64_t)*m_gmin;
+            int nc = 1;
+            while (nc < nf_prev && bl_sortable(pbt[2 * nc]) < gmin) nc++;
+            const bool redo = nc < nf_prev;
+            const int prank = pbrank[bl];
+            if (redo) {
+                if (primary && own) {
+                    c_mts[bl] = undo[bl]; c_mcode[bl] = undo[Tb + bl];
+                    if (prank >= 0 && prank < nf_prev) {
+                        const double ox = as_d(undo[2 * Tb + bl]), oy = as_d(undo[3 * Tb + bl]), ovx = as_d(undo[4 * Tb + bl]);
+                        const double ovy = as_d(undo[5 * Tb + bl]), ot0 = as_d(undo[6 * Tb + bl]), oarg = as_d(undo[8 * Tb + bl]);
+                        const int oi = (int)undo[9 * Tb + bl];
+                        const long long sq = (long long)undo[10 * Tb + bl];
+                        st_p0x[bl] = ox; st_p0y[bl] = oy; st_vx[bl] = ovx; st_vy[bl] = ovy; st_t0[bl] = ot0;
+                        c_ots[bl] = undo[7 * Tb + bl]; c_oarg[bl] = oarg; c_oidx[bl] = oi; c_seq[bl] = sq;
+                        __stcg(S.p0x + k, ox); __stcg(S.p0y + k, oy); __stcg(S.vx + k, ovx); __stcg(S.vy + k, ovy);
+                        __stcg(S.t0 + k, ot0); __stcg(S.obs_arg + k, oarg); __stcg(S.obs_idx + k, oi); __stcg(S.seq + k, sq);
+                    }
+                }
+                done = u_done; n_bb = u_nbb; now = u_now; prev_now = u_prev_now; win = u_win; mode = u_mode; kindmask = u_kind;
+                __syncthreads();
+            }
+            const int myrank_p = prank >= 0 && prank < nf_prev ? prank : -1;
+            const bool mine_p = myrank_p >= 0 && myrank_p < nc;
+            uint64_t f_ts, f_code;
+            int f_hit;
+            helper_pass(pbid, nc, myrank_p, mine_p, true, redo, f_ts, f_code, f_hit);
+            if (redo) {
+                if (H > 1) { fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit; }
+                __syncthreads();
+                if (primary && own)
+                    primary_apply(bx_b + qb * 2 * m_max, by_b + qb * 2 * m_max, bvx_b + qb * 2 * m_max, bvy_b + qb * 2 * m_max,
+                                  pbt, pbid, myrank_p, mine_p, f_ts, f_code, f_hit != 0, u_done, false);
+                advance_clock(pbt, r_info_b + qb * 4 * m_max, nc, nf_prev, u_nE);
+                if (prof_thread) prof[7]++;
+            }
+            // event log, simulation.py:590-594 / :626-631 payloads
+            if (want_log && cta == 0) {
+                const double *const pr_pay = r_pay_b + qb * 13 * m_max;
+                const int *const pr_info = r_info_b + qb * 4 * m_max;
+                for (int r = tid; r < nc; r += T) {
+                    const long long e = u_done + r;
+                    const double *pl = pr_pay + 13 * r;
+                    const bool bb = pr_info[4 * r + 2] != 0;
+                    P.log.t[e] = pl[12]; P.log.i[e] = pbid[2 * r];
+                    P.log.j[e] = bb ? (long long)pbid[2 * r + 1] : -1 - (long long)pr_info[4 * r + 1];
+                    if (P.log.payload) {
+                        double *o = P.log.payload + 12 * e;
+#pragma unroll
+                        for (int f = 0; f < 12; f++) o[f] = pl[f];
+                    }
+                }
+            }
+            pending = false;
+            if (redo) {
+                // start over from the corrected state: drop the collected keys
+                __syncthreads();
+                if (primary) pbrank[bl] = -1;
+                if (tid == 0) { misc[M_ECOUNT] = 0; misc[M_ACTION] = ACT_BATCH; misc[M_PCOUNT] = 0; }
+                if (tid < BL_R_POST) { pl_ts[tid] = ~0ull; pl_code[tid] = BL_CODE_END; }
+                __syncthreads();
+                continue;
+            }
+            if (primary) pbrank[bl] = -1;
+        }
+        if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
 
         // =========================== 3. analyse + resolve ======================================================
         // order and conflicts of the collected keys, one (i, j) pair per thread: entry j comes before entry i ->
@@ -800,141 +999,35 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
         }
         if (prof_thread) { const long long cs = clock64(); prof[10] += cs - c0; c0 = cs; }
-        if (nf > 1) {
+        {
             const uint64_t wmin = warp_min_u64(vmin);
             if (lane == 0 && wmin != ~0ull) atomicMin(m_viol, (unsigned long long)wmin);
-            __syncthreads();
-            if (ncta > 1) {
-                if (tid == 0) __stcg(P.viol + (size_t)par * BL_MAX_CTAS + cta, (uint64_t)*m_viol);
-                sync_all(P, epoch);
-                uint64_t hh = ~0ull;
-                for (int c = lane; c < ncta; c += 32) {
-                    const uint64_t v2 = __ldcg(P.viol + (size_t)par * BL_MAX_CTAS + c);
-                    hh = v2 < hh ? v2 : hh;
-                }
-                vmin = warp_min_u64(hh);
-            } else {
-                vmin = (uint64_t)*m_viol;
-            }
-            __syncthreads();
-            if (tid == 0) *m_viol = ~0ull;
-        } else {
-            vmin = ~0ull;
-            __syncthreads();  // the parked values of a ball come from all of its helpers' warps
         }
-        // collisions committed: the first one always, the others while they come before every violation
-        int nc = 1;
-        while (nc < nf && bl_sortable(bt[2 * nc]) < vmin) nc++;
-        if (prof_thread) { const long long c3 = clock64(); prof[2] += c3 - c0; c0 = c3; }
+        __syncthreads();  // all parked values and the CTA's violation minimum are in place
 
-        // =========================== 5. commit ===============================================================
-        const bool mine = myrank >= 0 && myrank < nc;  // my ball's own collision is committed
+        // =========================== 5. optimistic commit =====================================================
+        // as if nothing violated (nc = nf): candidates folded, states / mirrors / sequence numbers updated, so that
+        // the next round's keys can be posted together with this round's violation word -- ONE grid barrier per
+        // round.  The row stores and the log wait for the validation at the start of the next round.
         {
-            // helper h stores and folds the new values of the collisions r = h, h + H, ...
-            uint64_t f_ts = ts_inf, f_code = BL_CODE_NONE;
-            int f_hit = 0;
-            if (own) {
-                int q = -1;
-                const uint64_t mcode = c_mcode[bl];
-                if (!mine && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
-                for (int r = h; r < nc; r += H) {
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int j = 2 * r + u;
-                        const int x = bid[j];
-                        if (x < 0) continue;
-                        if (r == myrank) {
-                            // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
-                            if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
-                            continue;
-                        }
-                        if (mine && r < myrank) continue;  // that pair is re-solved at my (later) collision, from x's side
-                        // my cell in the row of the ball whose collision is the later one of the pair
-                        const double v = stash[(size_t)j * Tb + bl];
-                        __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
-                        if (x == q) f_hit = 1;
-                        if (v < BL_INF) {
-                            const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
-                            if (bl_key_less(vs, vc, f_ts, f_code)) { f_ts = vs; f_code = vc; }
-                        }
-                    }
-                }
-            }
+            const bool mine = myrank >= 0;
+            uint64_t f_ts, f_code;
+            int f_hit;
+            helper_pass(bid, nf, myrank, mine, false, true, f_ts, f_code, f_hit);
             if (H > 1) {
                 fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit;
                 __syncthreads();
             }
-            if (primary && own) {
-                uint64_t c_ts = f_ts, c_code = f_code;
-                bool partner_hit = f_hit != 0;
-                for (int g = 1; g < H; g++) {
-                    const uint64_t t2 = fold[2 * (g * Tb + bl)], c2 = fold[2 * (g * Tb + bl) + 1];
-                    if (bl_key_less(t2, c2, c_ts, c_code)) { c_ts = t2; c_code = c2; }
-                    partner_hit = partner_hit || fold_hit[g * Tb + bl] != 0;
-                }
-                const uint64_t mts = c_mts[bl], mcode = c_mcode[bl];
-                if (mine) {
-                    // my cover is emptied and refilled with the pairs solved at later collisions of the batch
-                    c_mts[bl] = c_code != BL_CODE_NONE ? c_ts : ts_inf; c_mcode[bl] = c_code;
-                    st_p0x[bl] = nx; st_p0y[bl] = ny; st_vx[bl] = nvx; st_vy[bl] = nvy; st_t0[bl] = nt0;
-                    c_ots[bl] = scratch[3 * bl];
-                    const double oarg = as_d(scratch[3 * bl + 1]);
-                    const int oi = (int)scratch[3 * bl + 2];
-                    c_oarg[bl] = oarg; c_oidx[bl] = oi;
-                    const long long sq = seq_base + done + myrank + 1;
-                    c_seq[bl] = sq;
-                    // keep the global mirror current: resolvers read ball states from it
-                    __stcg(S.p0x + k, nx); __stcg(S.p0y + k, ny); __stcg(S.vx + k, nvx); __stcg(S.vy + k, nvy);
-                    __stcg(S.t0 + k, nt0);
-                    __stcg(S.obs_arg + k, oarg); __stcg(S.obs_idx + k, oi);
-                    __stcg(S.seq + k, sq);
-                } else if (mcode == BL_CODE_STALE) {
-                    if (c_code != BL_CODE_NONE && c_ts < mts) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }  // strictly earlier: decisive
-                } else if (partner_hit) {
-                    // the entry that was my candidate has just been overwritten
-                    if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }
-                    else c_mcode[bl] = BL_CODE_STALE;  // the old time stays as a lower bound
-                } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
-                    c_mts[bl] = c_ts; c_mcode[bl] = c_code;
-                }
-            }
+            if (primary && own) primary_apply(bx, by, bvx, bvy, bt, bid, myrank, mine, f_ts, f_code, f_hit != 0, done, true);
         }
-        // event log, simulation.py:590-594 / :626-631 payloads
-        if (want_log && cta == 0) {
-            for (int r = tid; r < nc; r += T) {
-                const long long e = done + r;
-                const double *pl = r_pay + 13 * r;
-                const bool bb = r_info[4 * r + 2] != 0;
-                P.log.t[e] = pl[12]; P.log.i[e] = bid[2 * r];
-                P.log.j[e] = bb ? (long long)bid[2 * r + 1] : -1 - (long long)r_info[4 * r + 1];
-                if (P.log.payload) {
-                    double *o = P.log.payload + 12 * e;
-#pragma unroll
-                    for (int f = 0; f < 12; f++) o[f] = pl[f];
-                }
-            }
-        }
-        for (int r = 0; r < nc; r++) n_bb += r_info[4 * r + 2];
-        done += nc;
-        prev_now = now;
-        now = bt[2 * (nc - 1)];
-        // ---- next window ----
-        if (mode == MODE_ARGMIN) {
-            kindmask = KIND_BOTH;  // only the first event's kind was forced
-            if (!(win > 0.0)) {
-                const double gap = bl_sub(now, prev_now);
-                if (done >= 2 && gap > 0.0) win = bl_mul(gap, (double)P.target);
-            }
-            if (win > 0.0) mode = MODE_WINDOW;
-        } else {
-            if (nc < nf) win = bl_mul(win, 0.5);
-            else if (2 * nE < P.target) win = bl_mul(win, 1.5);
-            else if (nE > P.target + (P.target >> 1)) win = bl_mul(win, 0.75);
-        }
-        __syncthreads();
-        if (primary) brank[bl] = -1;
+        u_done = done; u_nbb = n_bb; u_now = now; u_prev_now = prev_now; u_win = win; u_mode = mode; u_kind = kindmask;
+        u_nE = nE;
+        advance_clock(bt, r_info, nf, nf, nE);
+        pending = true;
+        nf_prev = nf;
+        pb ^= 1;
         if (prof_thread) prof[6] += clock64() - c0;
-        // the next barrier (post) orders this round's global stores before anybody reads them
+        // the barrier of the next post orders this round's mirror stores before anybody reads them
     }
 
     // ---- write back the resident cache ------------------------------------------------------------------
