@@ -227,9 +227,9 @@ def bench_gas(args, device, fma):
                    "ctas_x_threads": list(_evolve_config(h, N)), "dot_fma": bool(fma)},
         "counts": {"ball_ball": n_bb, "ball_obstacle": n_bo, "stale_row_rescans": rescans},
         "phase_cycles_per_round": {k: prof[q] / max(prof[5], 1) for k, q in
-                                   (("post", 8), ("barrier_1", 9), ("collect_analyse_resolve", 0), ("solve", 10),
-                                    ("violation_exchange_barrier_2", 2), ("commit", 6), ("repair", 3))},
-        "repair_phases": prof[4], "rounds": prof[5], "reposted_rounds": prof[7],
+                                   (("post", 8), ("grid_barrier", 9), ("collect", 11), ("validate_and_row_stores", 2),
+                                    ("analyse_resolve", 0), ("solve", 10), ("optimistic_commit", 6), ("repair", 3))},
+        "repair_phases": prof[4], "rounds": prof[5], "reposted_or_redone_rounds": prof[7],
         "collisions_per_round": (n_bb + n_bo) / max(prof[5], 1),
         "build_seconds": build_s,
     }, cfg
@@ -431,7 +431,7 @@ def main():
         gas, _ = bench_gas(args, device, fma)
         line.update({k: gas[k] for k in ("value", "ms_per_step", "config", "roofline", "e2e", "clocks", "gpu_launches")})
         line["counts"] = gas["counts"]
-        for key in ("phase_cycles_per_round", "repair_phases", "rounds", "reposted_rounds", "collisions_per_round"):
+        for key in ("phase_cycles_per_round", "repair_phases", "rounds", "reposted_or_redone_rounds", "collisions_per_round"):
             line[key] = gas[key]
         line["table_build_seconds"] = gas["build_seconds"]
         ens_steps = max(1, min(args.steps, 3))

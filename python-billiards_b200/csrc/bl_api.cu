@@ -52,7 +52,6 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
     if ((e = cudaMalloc(&h->d_bar, 64)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMalloc(&h->d_post, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_POST_WORDS)) != cudaSuccess)
         return bl_check_cuda(h, e, "cudaMalloc");
-    if ((e = cudaMalloc(&h->d_viol, sizeof(uint64_t) * 2 * BL_MAX_CTAS)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMalloc(&h->d_stale, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_MAX_THREADS)) != cudaSuccess)
         return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMalloc(&h->d_partial, sizeof(uint64_t) * 2 * BL_MAX_CTAS * BL_RCHUNK * 2)) != cudaSuccess)
@@ -73,7 +72,6 @@ int bl_destroy(bl_handle *h) {
     if (h->d_result) cudaFree(h->d_result);
     if (h->d_bar) cudaFree(h->d_bar);
     if (h->d_post) cudaFree(h->d_post);
-    if (h->d_viol) cudaFree(h->d_viol);
     if (h->d_stale) cudaFree(h->d_stale);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->h_result) cudaFreeHost(h->h_result);

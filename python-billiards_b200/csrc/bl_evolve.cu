@@ -14,16 +14,20 @@
 // times of its two balls) comes earlier than e2.  That condition can be CHECKED exactly, so a round works on a
 // whole window of pending collisions at once:
 //
-//   1. post      every ball whose candidate key (time, code) lies below the window end `theta` is posted; one
-//                grid barrier later every CTA holds the same complete list of keys < theta;
-//   2. analyse   warp 0 sorts the list in registers and cuts it at the first entry that shares a ball with an
-//                earlier one (or is only a lower bound); one lane per remaining collision resolves it
-//                (elastic_collision / obstacle reflection);
-//   3. solve     every ball is solved against every ball of the batch -- with its state as of just before that
+//   1. post      every ball whose candidate key (time, code) lies below the window end `theta` is posted, together
+//                with the violation word of the previous batch (step 5); ONE grid barrier later every CTA holds the
+//                same complete list of keys < theta;
+//   2. validate  the previous batch was committed optimistically; if its violation word says that nothing it
+//                produced came too early (the normal case) only its table rows and log records are left to write,
+//                otherwise the commit is rolled back, redone for the valid prefix, and the keys are posted again;
+//   3. analyse   all threads rank the keys pairwise, warp 0 sorts them into its lanes and cuts the list at the
+//                first entry that shares a ball with an earlier one (or is only a lower bound); one lane per
+//                remaining collision resolves it (elastic_collision / obstacle reflection);
+//   4. solve     every ball is solved against every ball of the batch -- with its state as of just before that
 //                collision -- and the values are parked in shared memory; any new key that would come earlier
 //                than a collision of the batch is a violation;
-//   4. commit    the batch prefix below the earliest violation (all of it, normally) is committed: table rows
-//                stored, candidates folded, states updated, log written.  The rest is re-posted.
+//   5. commit    optimistically, as if nothing violated: candidates folded, states / mirrors / sequence numbers
+//                updated, so that the next keys can be posted right away.
 //
 // Collision 1 of a round is the true global minimum, so every round commits at least what the reference's
 // iteration would; the committed sequence, every table entry and every state bit are the reference's.
@@ -77,7 +81,6 @@ struct Params {
     double window;  // initial window length (0: unknown)
     unsigned *bar;  // [0] grid barrier counter, [4] stale-list length (zero at launch)
     uint64_t *post; // [2][BL_MAX_CTAS][BL_POST_WORDS]
-    uint64_t *viol; // [2][BL_MAX_CTAS]
     uint64_t *stale_list; // [BL_MAX_CTAS * BL_MAX_THREADS][2] (ball, seq) of the candidates under repair
     uint64_t *partial;    // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
     double repair_horizon; // stale candidates within this many windows of `now` are repaired together
@@ -101,6 +104,9 @@ struct Layout {
     int mass, radius, oarg;           // [Tb] doubles
     int oidx, brank, rclass;          // [Tb] ints (brank: [2][Tb])
     int undo;                         // [11][Tb] state before the optimistic commit of the last batch
+    int bts;                          // [2][m_max] sortable collision times of the batch, by rank
+    int obsp;                         // [H][3][Tb] next-obstacle partial minima of the helpers (t, arg, index)
+    int hl;                           // ints: [Tb] count, [Tb] partner-hit flag, [Tb][BL_HL_CAP] finite new values of a ball
     int dirty;                        // [Tb] ints
     int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
     int fold;                         // [H][Tb][2] partial candidate of each helper + [H][Tb] ints partner-hit
@@ -130,6 +136,9 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.mass = w; w += Tb; L.radius = w; w += Tb; L.oarg = w; w += Tb;
     L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += Tb; L.rclass = w; w += (Tb + 1) / 2;
     L.undo = w; w += 11 * Tb;
+    L.bts = w; w += 2 * m_max;
+    L.obsp = w; w += 3 * H * Tb;
+    L.hl = w; w += (Tb * (BL_HL_CAP + 2) + 1) / 2;
     L.dirty = w; w += (Tb + 1) / 2;
     L.scratch = w; w += 3 * Tb;
     L.fold = w; w += H * Tb * 2 + (H * Tb + 1) / 2;
@@ -246,6 +255,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double *wq = reinterpret_cast<double *>(sm + L.wq);
     const bl_obstacle *obs = reinterpret_cast<const bl_obstacle *>(sm + L.obs);
     int *misc = reinterpret_cast<int *>(sm + L.misc);
+    uint64_t *const bts_b = sm + L.bts;
+    uint64_t *const obsp = sm + L.obsp;
+    int *const hl_cnt = reinterpret_cast<int *>(sm + L.hl), *const ph = hl_cnt + Tb, *const hl = ph + Tb;
     unsigned long long *m_viol = reinterpret_cast<unsigned long long *>(sm + L.misc + M_VIOL);
     unsigned long long *m_gmin = reinterpret_cast<unsigned long long *>(sm + L.misc + M_GMIN);
 
@@ -275,6 +287,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             c_ots[bl] = ts_inf; c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE;
         }
         brank_b[bl] = -1; brank_b[Tb + bl] = -1;
+        hl_cnt[bl] = 0; ph[bl] = 0;
     }
     const double rs11 = (K == 1 && n > 0) ? S.rsum2[0] : 0.0;
     double *const myrow = S.toi + (size_t)(own ? k : 0) * (size_t)S.pitch;
@@ -346,8 +359,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     // primary half: combine the helpers' partial candidates and update the ball
     auto primary_apply = [&](const double *Bx, const double *By, const double *Bvx, const double *Bvy, const double *Bt,
                              const int *Bbid, const int myrank_, const bool mine_, uint64_t c_ts, uint64_t c_code,
-                             bool partner_hit, const long long done_base, const bool save_undo) {
-        for (int g = 1; g < H; g++) {
+                             bool partner_hit, const long long done_base, const bool save_undo, const bool combine) {
+        for (int g = 1; combine && g < H; g++) {
             const uint64_t t2 = fold[2 * (g * Tb + bl)], c2 = fold[2 * (g * Tb + bl) + 1];
             if (bl_key_less(t2, c2, c_ts, c_code)) { c_ts = t2; c_code = c2; }
             partner_hit = partner_hit || fold_hit[g * Tb + bl] != 0;
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     };
     // clock, counters and window after nc_ of the nf_ collisions of a batch have been committed
     auto advance_clock = [&](const double *Bt, const int *Br_info, const int nc_, const int nf_, const int nE_) {
-        for (int r = 0; r < nc_; r++) n_bb += Br_info[4 * r + 2];
+        n_bb += Br_info[4 * (nc_ - 1) + 3];
         done += nc_;
         prev_now = now;
         now = Bt[2 * (nc_ - 1)];
@@ -421,7 +434,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         int *const bid = bid_b + pb * 2 * m_max, *const brc = brc_b + pb * 2 * m_max;
         double *const r_pay = r_pay_b + pb * 13 * m_max;
         int *const r_info = r_info_b + pb * 4 * m_max, *const brank = brank_b + pb * Tb;
+        uint64_t *const bts = bts_b + pb * m_max;
         const int qb = pb ^ 1;
+        const uint64_t *const pbts = bts_b + qb * m_max;
         const double *const pbt = bt_b + qb * 2 * m_max;
         const int *const pbid = bid_b + qb * 2 * m_max;
         int *const pbrank = brank_b + qb * Tb;
@@ -499,7 +514,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         }
         par ^= 1;
         __syncthreads();
-        if (prof_thread) prof[11] += clock64() - c0;
+        if (prof_thread) { const long long cc = clock64(); prof[11] += cc - c0; c0 = cc; }
 
         // =========================== 2b. validate the previous batch ===========================================
         // It was committed optimistically (candidates, states, mirrors) before this round's keys were posted; its
@@ -508,8 +523,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // from a state that never existed -- are thrown away.
         if (pending) {
             const uint64_t gmin = (uint64_t)*m_gmin;
-            int nc = 1;
-            while (nc < nf_prev && bl_sortable(pbt[2 * nc]) < gmin) nc++;
+            // committed: the first collision always, the others while they come before every violation (the times
+            // are sorted, so that is a count)
+            int nc = __popc(__ballot_sync(0xffffffffu, lane < nf_prev && pbts[lane < nf_prev ? lane : 0] < gmin)) +
+                     __popc(__ballot_sync(0xffffffffu, lane + 32 < nf_prev && pbts[lane + 32 < nf_prev ? lane + 32 : 0] < gmin));
+            if (nc < 1) nc = 1;
             const bool redo = nc < nf_prev;
             const int prank = pbrank[bl];
             if (redo) {
@@ -539,7 +557,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 __syncthreads();
                 if (primary && own)
                     primary_apply(bx_b + qb * 2 * m_max, by_b + qb * 2 * m_max, bvx_b + qb * 2 * m_max, bvy_b + qb * 2 * m_max,
-                                  pbt, pbid, myrank_p, mine_p, f_ts, f_code, f_hit != 0, u_done, false);
+                                  pbt, pbid, myrank_p, mine_p, f_ts, f_code, f_hit != 0, u_done, false, true);
                 advance_clock(pbt, r_info_b + qb * 4 * m_max, nc, nf_prev, u_nE);
                 if (prof_thread) prof[7]++;
             }
@@ -682,7 +700,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             const double ax = bl_advance(q0x, wvx, t, wt0), ay = bl_advance(q0y, wvy, t, wt0);
                             double nvx = wvx, nvy = wvy;
                             st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, wvx, wvy, qarg, nvx, nvy) : BL_EASSERT;
-                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t;
+                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t; bts[r] = ts;
                             bid[2 * r] = a; brc[2 * r] = rca;
                             bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
                             pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
@@ -702,7 +720,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             bl_remap_masses(m1, m2);
                             double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
                             st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
-                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t;
+                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t; bts[r] = ts;
                             bid[2 * r] = a; brc[2 * r] = rca;
                             bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
                             bid[2 * r + 1] = b; brc[2 * r + 1] = rcb;
@@ -720,6 +738,15 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     const int er = __reduce_min_sync(0xffffffffu, er_mine);
                     if (er < nf) nf = er;
                     if (nf == 0) action = ACT_ERROR;
+                    // running count of ball-ball collisions by rank
+                    __syncwarp();
+                    {
+                        const unsigned b0m = __ballot_sync(0xffffffffu, lane < nf && r_info[4 * (lane < nf ? lane : 0) + 2] != 0);
+                        const unsigned b1m = __ballot_sync(0xffffffffu, lane + 32 < nf && r_info[4 * (lane + 32 < nf ? lane + 32 : 0) + 2] != 0);
+                        const unsigned le_mask = lt_mask | (1u << lane);
+                        if (lane < nf) r_info[4 * lane + 3] = __popc(b0m & le_mask);
+                        if (lane + 32 < nf) r_info[4 * (lane + 32) + 3] = __popc(b0m) + __popc(b1m & le_mask);
+                    }
                 }
                 if (lane == 0) { s_ts[0] = ts0; s_code[0] = cd0; }  // the front entry, for the stop stages
             }
@@ -913,22 +940,30 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // helper h takes the collisions r = h, h + H, ...
         int myrank = brank[bl];
         if (myrank >= nf) myrank = -1;
-        const uint64_t vbound = bl_sortable(bt[2 * (nf - 1)]);  // time of the last collision of the batch
+        const uint64_t vbound = bts[nf - 1];  // time of the last collision of the batch
         uint64_t vmin = ~0ull;
         const double p0x = st_p0x[bl], p0y = st_p0y[bl], vx = st_vx[bl], vy = st_vy[bl], t0 = st_t0[bl];
         double nx = 0, ny = 0, nvx = 0, nvy = 0, nt0 = 0;   // my state after my own collision (batch balls only)
+        int qpart = -1;  // partner of my current candidate (a ball of the batch overwrites that entry)
         if (own && myrank >= 0) {
             const int myj = bid[2 * myrank] == k ? 2 * myrank : 2 * myrank + 1;
             nx = bx[myj]; ny = by[myj]; nvx = bvx[myj]; nvy = bvy[myj]; nt0 = bt[myj];
-            if (h == H - 1) {
-                // my next obstacle after the collision, simulation.py:490-495 / :545-547
-                double ot, oarg;
-                int oi;
-                bl_next_obstacle<FMA>(obs, n_obs, S.rsum2_obs, K, myrc, nx, ny, nvx, nvy, c_radius[bl], nt0, ot, oi, oarg);
-                const uint64_t n_ots = bl_sortable(ot);
-                scratch[3 * bl] = n_ots; scratch[3 * bl + 1] = as_u(oarg); scratch[3 * bl + 2] = (uint64_t)(unsigned)oi;
-                if (n_ots <= vbound && myrank < nf - 1) vmin = n_ots;
+            // my next obstacle after the collision, simulation.py:490-495 / :545-547: helper h looks at the obstacles
+            // h, h + H, ... (list order, strict <); the primary combines the partial minima
+            double t_min = BL_INF, arg_min = 0.0;
+            int q_min = -1;
+            const double radius = c_radius[bl];
+            for (int q = h; q < n_obs; q += H) {
+                double a;
+                const double rs = obs[q].kind == BL_OBS_DISK ? S.rsum2_obs[(size_t)q * K + myrc] : 0.0;
+                const double t = bl_obstacle_toi<FMA>(obs[q], nx, ny, nvx, nvy, radius, rs, a);
+                if (t < t_min) { t_min = t; q_min = q; arg_min = a; }
             }
+            obsp[(h * 3 + 0) * Tb + bl] = as_u(t_min); obsp[(h * 3 + 1) * Tb + bl] = as_u(arg_min);
+            obsp[(h * 3 + 2) * Tb + bl] = (uint64_t)(unsigned)q_min;
+        } else if (own) {
+            const uint64_t mcode = c_mcode[bl];
+            if (mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) qpart = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
         }
         // Pass 1, branch-free: advance my ball to the collision time once, then form the quadratic of
         // physics.py:33-54 against both balls of the collision.  Only ~5 % of the pairs get past the two early
@@ -951,6 +986,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     const double st0 = after ? nt0 : t0;
                     const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
                     const int x1 = bid[2 * r + 1];
+                    if (qpart >= 0 && (bid[2 * r] == qpart || x1 == qpart)) ph[bl] = 1;
                     {
                         const int j = 2 * r;
                         const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
@@ -985,6 +1021,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         const double t1 = bl_div(q_c[i], bl_add(-q_b[i], bl_sqrt(q_d[i])));
                         const double v = bl_add(bt[j], t1 >= BL_T_EPS ? t1 : BL_INF);
                         stash[(size_t)j * Tb + (dst & 0xffff)] = v;
+                        if (v < BL_INF) {  // the few finite values of a ball: all its optimistic fold has to look at
+                            const int ob = dst & 0xffff;
+                            const int slot = atomicAdd(&hl_cnt[ob], 1);
+                            if (slot < BL_HL_CAP) hl[ob * BL_HL_CAP + slot] = j;
+                        }
                         const uint64_t vs = bl_sortable(v);
                         if (vs <= vbound && (j >> 1) < nf - 1) vmin = vs < vmin ? vs : vmin;
                     }
@@ -1009,16 +1050,38 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // as if nothing violated (nc = nf): candidates folded, states / mirrors / sequence numbers updated, so that
         // the next round's keys can be posted together with this round's violation word -- ONE grid barrier per
         // round.  The row stores and the log wait for the validation at the start of the next round.
-        {
+        if (primary && own) {
             const bool mine = myrank >= 0;
-            uint64_t f_ts, f_code;
-            int f_hit;
-            helper_pass(bid, nf, myrank, mine, false, true, f_ts, f_code, f_hit);
-            if (H > 1) {
-                fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit;
-                __syncthreads();
+            if (mine) {
+                // combine the helpers' next-obstacle minima (first obstacle in list order among equal times)
+                double t_min = BL_INF, arg_min = 0.0;
+                int q_min = -1;
+                for (int g = 0; g < H; g++) {
+                    const double t = as_d(obsp[(g * 3 + 0) * Tb + bl]);
+                    const int qg = (int)obsp[(g * 3 + 2) * Tb + bl];
+                    if (qg >= 0 && (t < t_min || (t == t_min && qg < q_min))) { t_min = t; q_min = qg; arg_min = as_d(obsp[(g * 3 + 1) * Tb + bl]); }
+                }
+                const uint64_t n_ots = bl_sortable(bl_add(bt[2 * myrank], t_min));
+                scratch[3 * bl] = n_ots; scratch[3 * bl + 1] = as_u(arg_min); scratch[3 * bl + 2] = (uint64_t)(unsigned)q_min;
+                if (n_ots <= vbound && myrank < nf - 1) atomicMin(m_viol, (unsigned long long)n_ots);
             }
-            if (primary && own) primary_apply(bx, by, bvx, bvy, bt, bid, myrank, mine, f_ts, f_code, f_hit != 0, done, true);
+            // fold the finite new values of my ball (listed by the solve pass; all of them if the list overflowed)
+            uint64_t c_ts = ts_inf, c_code = BL_CODE_NONE;
+            const int cnt = hl_cnt[bl];
+            const int nscan = cnt <= BL_HL_CAP ? cnt : 2 * nf;
+            for (int i = 0; i < nscan; i++) {
+                const int j = cnt <= BL_HL_CAP ? hl[bl * BL_HL_CAP + i] : i;
+                const int r = j >> 1, x = bid[j];
+                if (x < 0 || r == myrank || (mine && r < myrank)) continue;
+                const double v = stash[(size_t)j * Tb + bl];
+                if (v < BL_INF) {
+                    const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
+                    if (bl_key_less(vs, vc, c_ts, c_code)) { c_ts = vs; c_code = vc; }
+                }
+            }
+            const bool partner_hit = ph[bl] != 0;
+            hl_cnt[bl] = 0; ph[bl] = 0;
+            primary_apply(bx, by, bvx, bvy, bt, bid, myrank, mine, c_ts, c_code, partner_hit, done, true, false);
         }
         u_done = done; u_nbb = n_bb; u_now = now; u_prev_now = prev_now; u_win = win; u_mode = mode; u_kind = kindmask;
         u_nE = nE;
@@ -1147,7 +1210,7 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.target = target;
     // the window length found by the previous launch on this system is a good first guess
     P.window = (h->window_n == s->n && h->window_sys == (const void *)s->toi) ? h->window : 0.0;
-    P.bar = h->d_bar; P.post = h->d_post; P.viol = h->d_viol;
+    P.bar = h->d_bar; P.post = h->d_post;
     P.stale_list = h->d_stale; P.partial = h->d_partial;
     P.repair_horizon = h->repair_horizon;
     size_t smem = (size_t)make_layout(P.Tb, P.H, P.m_max, s->n_obstacles).words * 8;

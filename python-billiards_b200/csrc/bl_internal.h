@@ -18,7 +18,6 @@ struct bl_handle {
     // event kernel exchange buffers (global memory; see bl_evolve.cu)
     unsigned *d_bar;          // grid barrier counter
     uint64_t *d_post;         // [2][BL_MAX_CTAS][BL_POST_WORDS] keys posted by each CTA
-    uint64_t *d_viol;         // [2][BL_MAX_CTAS] earliest violating new key of each CTA
     uint64_t *d_stale;        // [BL_MAX_CTAS * BL_MAX_THREADS][2] candidates under repair
     uint64_t *d_partial;      // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
     double repair_horizon;    // in windows (BL_REPAIR_HORIZON, default 8)
@@ -33,12 +32,13 @@ struct bl_handle {
 
 #define BL_MAX_THREADS 1024
 #define BL_MAX_CTAS 160       // >= SM count
-#define BL_POST_WORDS 16      // header + BL_R_POST keys of 2 words
+#define BL_POST_WORDS 16      // header, violation word, BL_R_POST keys of 2 words
 #define BL_R_POST 6           // keys one CTA may post per round
 #define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
 #define BL_SORT_CAP 64        // keys a window round sorts (two per lane of warp 0); more -> the window is halved
 #define BL_M_MAX 48           // collisions committed per round, at most
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
+#define BL_HL_CAP 6           // finite new values of one ball listed per round (more -> that ball scans all of them)
 #define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
 
