@@ -58,7 +58,7 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
         return bl_check_cuda(h, e, "cudaMalloc");
     {
         const char *hz = getenv("BL_REPAIR_HORIZON");
-        h->repair_horizon = hz ? atof(hz) : 8.0;
+        h->repair_horizon = hz ? atof(hz) : 16.0;
         const char *eg = getenv("BL_ENSEMBLE_GENERIC");
         h->ensemble_generic = eg ? atoi(eg) : 0;
     }

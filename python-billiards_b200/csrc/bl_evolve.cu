@@ -1204,9 +1204,9 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     // m^2 / n, the synchronisation cost per collision falls like 1 / m (measured optimum ~ sqrt(n / 8))
     int target = 1;
     while ((long long)(target + 1) * (target + 1) * 8 <= (long long)s->n) target++;
-    if (target > P.m_max - 4) target = P.m_max - 4;
+    if (target > P.m_max + 2) target = P.m_max + 2;  // keys, of which about a third are the same pair posted twice
     if (target < 1) target = 1;
-    if (h->target_override > 0) target = h->target_override < P.m_max ? h->target_override : P.m_max;
+    if (h->target_override > 0) target = h->target_override < BL_SORT_CAP - 4 ? h->target_override : BL_SORT_CAP - 4;
     P.target = target;
     // the window length found by the previous launch on this system is a good first guess
     P.window = (h->window_n == s->n && h->window_sys == (const void *)s->toi) ? h->window : 0.0;
