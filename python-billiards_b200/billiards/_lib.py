@@ -84,6 +84,7 @@ SIGNATURES = {
     "bl_launch_count": (ctypes.c_int64, [_H]),
     "bl_evolve_config": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "bl_set_batch_target": (ctypes.c_int, [_H, ctypes.c_int]),
+    "bl_set_small_kernel": (ctypes.c_int, [_H, ctypes.c_int]),
 }
 
 _lib = None

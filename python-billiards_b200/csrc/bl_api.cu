@@ -236,6 +236,12 @@ int bl_evolve_config(const bl_handle *h, int n, int *ctas, int *threads) {
     return bl_evolve_pick_config(h, n, ctas, threads, &sync_mode);
 }
 
+int bl_set_small_kernel(bl_handle *h, int enable) {
+    if (!h) return BL_EINVAL;
+    h->small_kernel_off = enable ? 0 : 1;
+    return BL_OK;
+}
+
 int bl_set_batch_target(bl_handle *h, int target) {
     if (!h || target < 0) return BL_EINVAL;
     h->target_override = target;

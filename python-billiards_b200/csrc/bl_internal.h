@@ -26,6 +26,7 @@ struct bl_handle {
     int window_n;
     const void *window_sys;
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
+    int small_kernel_off;     // bl_set_small_kernel(h, 0): systems of <= 32 balls also take the grid-wide event kernel
     int ensemble_generic;     // BL_ENSEMBLE_GENERIC=1: always use the generic (list in shared memory) ensemble kernel
     char err[512];
 };
@@ -38,6 +39,8 @@ struct bl_handle {
 #define BL_SORT_CAP 64        // keys a window round sorts (two per lane of warp 0); more -> the window is halved
 #define BL_M_MAX 48           // collisions committed per round, at most
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
+#define BL_SMALL_MAX_BALLS 32  // systems up to this size run in the one-warp kernel (bl_evolve_small.cu)
+#define BL_SMALL_MAX_OBS 32
 #define BL_HL_CAP 6           // finite new values of one ball listed per round (more -> that ball scans all of them)
 #define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
@@ -48,6 +51,8 @@ int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what);
 // bl_evolve.cu
 int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st);
+int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
+                           int first_kind, const bl_log *log, int query_only, cudaStream_t st);
 int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode);
 // bl_table.cu
 int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st);

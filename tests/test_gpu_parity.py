@@ -223,6 +223,32 @@ def test_stops_inside_a_batch(billiards, oracle):
     assert_bits_equal(np.concatenate(a.toi_table), np.concatenate(b.toi_table), "toi_table")
 
 
+def test_small_systems_through_the_grid_kernel(billiards, golden):
+    """Systems of <= 32 balls normally run in the one-warp kernel; the grid-wide kernel must give the same bits."""
+    from billiards import _lib
+    g = golden("pool")
+    fma = bool(g["dot_fma"])
+    h = _lib.get_handle(None, fma)
+    h.check(h.lib.bl_set_small_kernel(h.h, 0))
+    try:
+        bld = build(billiards, workloads.pool(), fma)
+        counts, (t, i, j, p) = bld.evolve_events(10**9, end_time=100.0, log_capacity=512, payload=True)
+        assert counts == (167, 248)
+        assert_bits_equal(t, g["log_t"])
+        assert i.tolist() == g["log_i"].tolist() and j.tolist() == g["log_j"].tolist()
+        assert_bits_equal(p, g["log_payload"], "callback payloads")
+        assert_bits_equal(bld.balls_position, g["end_pos"])
+        assert_bits_equal(np.concatenate(bld.toi_table), g["end_toi_tri"], "toi_table")
+        gg = golden("galperin")
+        gal = build(billiards, workloads.galperin(), fma)
+        _, (t, i, j) = gal.evolve_events(20000, log_capacity=20000)
+        assert_bits_equal(t, gg["log_t"])
+        assert i.tolist() == gg["log_i"].tolist() and j.tolist() == gg["log_j"].tolist()
+        assert gal.evolve(16) == (157080 - int((gg["log_j"] >= 0).sum()), 157079 - int((gg["log_j"] < 0).sum()))
+    finally:
+        h.check(h.lib.bl_set_small_kernel(h.h, 1))
+
+
 def test_stop_resume_is_bit_stable(billiards, oracle):
     """tests/test_simulation.py:461-502: 300 partial evolves == one evolve, exactly; and == the oracle."""
     from billiards import _lib
