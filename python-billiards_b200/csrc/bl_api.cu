@@ -46,7 +46,6 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
                             prop.major, prop.minor);
     h->sm_count = prop.multiProcessorCount;
     h->max_smem_optin = prop.sharedMemPerBlockOptin;
-    h->max_cluster = 16;
     if ((e = cudaMalloc(&h->d_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
     if ((e = cudaMallocHost(&h->h_result, sizeof(bl_result))) != cudaSuccess) return bl_check_cuda(h, e, "cudaMallocHost");
     if ((e = cudaMalloc(&h->d_bar, 64)) != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double now = P.time;   // Billiard.time: time of the last committed collision
     double prev_now = P.time;
     double win = P.window;
-    int mode = (P.first_kind != BL_ANY || P.query_only || !(win > 0.0)) ? MODE_ARGMIN : MODE_WINDOW;
+    // target 1: always the exact argmin, one collision per round -- the reference's schedule
+    int mode = (P.first_kind != BL_ANY || P.query_only || !(win > 0.0) || P.target <= 1) ? MODE_ARGMIN : MODE_WINDOW;
     int kindmask = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
     int final_stage = P.query_only ? 1 : 0;  // 0: event loop, 1: report next ball-ball, 2: report next ball-obstacle
     if (final_stage == 1) kindmask = KIND_BB;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 const double gap = bl_sub(now, prev_now);
                 if (done >= 2 && gap > 0.0) win = bl_mul(gap, (double)P.target);
             }
-            if (win > 0.0) mode = MODE_WINDOW;
+            if (win > 0.0 && P.target > 1) mode = MODE_WINDOW;
         } else {
             if (nc_ < nf_) win = bl_mul(win, 0.5);
             else if (2 * nE_ < P.target) win = bl_mul(win, 1.5);

@@ -8,7 +8,6 @@ struct bl_handle {
     int device;
     int dot_fma;
     int sm_count;
-    int max_cluster;          // largest cluster size the event kernel may use on this device
     size_t max_smem_optin;
     bl_result *d_result;      // device result block
     bl_result *h_result;      // pinned host mirror

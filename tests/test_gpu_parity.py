@@ -223,6 +223,43 @@ def test_stops_inside_a_batch(billiards, oracle):
     assert_bits_equal(np.concatenate(a.toi_table), np.concatenate(b.toi_table), "toi_table")
 
 
+def test_batched_rounds_equal_one_at_a_time_over_a_long_run(billiards):
+    """120 000 collisions of the 16384-ball gas: windows of ~24 collisions per round (with their rollbacks and repair
+    phases) against the same kernel committing ONE collision per round, which is the reference's schedule.  Far beyond
+    what the CPU oracle can reach; event log, state and table must be identical bit for bit."""
+    from billiards import _lib
+    import hashlib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.dense_gas(128)
+    n_events = 120000
+    runs = []
+    for target in (0, 1):
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            counts, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        rounds = int(bld.last_result.prof[5])
+        digest = hashlib.sha256(t.tobytes() + i.tobytes() + j.tobytes()).hexdigest()
+        runs.append((counts, digest, bld.balls_velocity.copy(), bld.balls_initial_position.copy(),
+                     bld._balls_toi.copy(), bld.time, rounds))
+    assert runs[0][6] < n_events / 8 and runs[1][6] >= n_events      # batched vs one collision per round
+    assert runs[0][0] == runs[1][0] and sum(runs[0][0]) == n_events
+    assert runs[0][1] == runs[1][1], "event logs differ"
+    assert_bits_equal(runs[0][2], runs[1][2], "velocities")
+    assert_bits_equal(runs[0][3], runs[1][3], "initial positions")
+    assert_bits_equal(runs[0][4], runs[1][4], "_balls_toi")
+    assert runs[0][5] == runs[1][5]
+    # physics sanity of the long run: energy conserved (equal masses, elastic), nobody left the box
+    v = runs[0][2]
+    assert abs(float((v * v).sum()) / cfg.n - 1.0) < 1e-9
+    p = runs[0][3]
+    r = float(cfg.radius[0])
+    assert p.min() >= r - 1e-9 and p.max() <= 128.0 - r + 1e-9
+
+
 def test_small_systems_through_the_grid_kernel(billiards, golden):
     """Systems of <= 32 balls normally run in the one-warp kernel; the grid-wide kernel must give the same bits."""
     from billiards import _lib
