@@ -552,7 +552,19 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             const bool mine_p = myrank_p >= 0 && myrank_p < nc;
             uint64_t f_ts, f_code;
             int f_hit;
-            helper_pass(pbid, nc, myrank_p, mine_p, true, redo, f_ts, f_code, f_hit);
+            if (!redo && myrank_p < 0) {
+                // not a ball of that batch: every parked value is mine to store, four in flight
+                f_ts = ts_inf; f_code = BL_CODE_NONE; f_hit = 0;
+                if (own) {
+#pragma unroll 4
+                    for (int j = h; j < 2 * nc; j += H) {
+                        const int x = pbid[j];
+                        if (x >= 0) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[(size_t)j * Tb + bl]);
+                    }
+                }
+            } else {
+                helper_pass(pbid, nc, myrank_p, mine_p, true, redo, f_ts, f_code, f_hit);
+            }
             if (redo) {
                 if (H > 1) { fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit; }
                 __syncthreads();
@@ -599,19 +611,27 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         {
             const int nr = misc[M_ECOUNT];
             if (mode == MODE_WINDOW && nr > 1 && nr <= BL_SORT_CAP) {
-                for (int p = tid; p < nr * nr; p += T) {
-                    const int i = p / nr, j = p - i * nr;
-                    const uint64_t ti = e_ts[i], ci = e_code[i], tj = e_ts[j], cj = e_code[j];
-                    if (i != j && (bl_key_less(tj, cj, ti, ci) || (tj == ti && cj == ci && j < i))) {
-                        atomicAdd(&a_rank[i], 1);
-                        int a, b, a2, b2;
-                        key_balls(ci, a, b);
-                        key_balls(cj, a2, b2);
-                        if (a >= 0 && a2 >= 0) {
-                            if (a2 == a && b2 == b) atomicOr(&a_flag[i], F_DUP);
-                            else if (a2 == a || a2 == b || (b2 >= 0 && (b2 == a || b2 == b))) atomicOr(&a_flag[i], F_CONFLICT);
-                        }
-                    }
+                // lane l holds entries l and l + 32; a warp takes entry i, every lane says whether its entries come
+                // before i and whether they share a ball with it: rank and flags of i by ballot
+                const bool h0 = lane < nr, h1 = lane + 32 < nr;
+                const uint64_t t0e = h0 ? e_ts[lane] : ~0ull, c0e = h0 ? e_code[lane] : BL_CODE_END;
+                const uint64_t t1e = h1 ? e_ts[lane + 32] : ~0ull, c1e = h1 ? e_code[lane + 32] : BL_CODE_END;
+                int a0, b0, a1, b1;
+                key_balls(c0e, a0, b0);
+                key_balls(c1e, a1, b1);
+                for (int i = warp; i < nr; i += nwarps) {
+                    const uint64_t ti = e_ts[i], ci = e_code[i];
+                    int a, b;
+                    key_balls(ci, a, b);
+                    const bool p0 = h0 && lane != i && (bl_key_less(t0e, c0e, ti, ci) || (t0e == ti && c0e == ci && lane < i));
+                    const bool p1 = h1 && lane + 32 != i && (bl_key_less(t1e, c1e, ti, ci) || (t1e == ti && c1e == ci && lane + 32 < i));
+                    const bool s0 = p0 && a >= 0 && a0 >= 0, s1 = p1 && a >= 0 && a1 >= 0;
+                    const bool d0 = s0 && a0 == a && b0 == b, d1 = s1 && a1 == a && b1 == b;
+                    const bool x0 = s0 && !d0 && (a0 == a || a0 == b || (b0 >= 0 && (b0 == a || b0 == b)));
+                    const bool x1 = s1 && !d1 && (a1 == a || a1 == b || (b1 >= 0 && (b1 == a || b1 == b)));
+                    const int rk = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
+                    const bool dup = __any_sync(0xffffffffu, d0 || d1), conf = __any_sync(0xffffffffu, x0 || x1);
+                    if (lane == 0) { a_rank[i] = rk; a_flag[i] = (dup ? F_DUP : 0) | (conf ? F_CONFLICT : 0); }
                 }
                 __syncthreads();
             }
