@@ -335,6 +335,64 @@ def test_recompute_scenario(billiards, golden):
     check(b, "s5")
 
 
+@pytest.mark.parametrize("n_side,grid_kernel_small", [(12, False), (48, False), (4, True)])
+def test_edits_and_new_balls_between_launches(billiards, oracle, n_side, grid_kernel_small):
+    """recompute_toi after in-place edits and add_ball on a system that has already evolved -- through the cluster
+    (144 balls), the grid (2304 balls) and, with the one-warp kernel switched off, 16 balls in the grid-wide kernel:
+    the table mirror refresh (bl_symmetrize), the candidate rebuild and the sequence numbers have to line up."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.dense_gas(n_side, seed=5, phi=0.3)
+    n1 = 900 if n_side > 4 else 120
+    if grid_kernel_small:
+        h.check(h.lib.bl_set_small_kernel(h.h, 0))
+    try:
+        bld = build(billiards, cfg, fma)
+        ref = cfg.build_oracle(oracle, dot_fma=fma, flags=oracle.FAST_ROWMIN)
+
+        def step(k):
+            ref.clear_log()
+            ref.enable_log(k)
+            ref.evolve(INF, max_events=k)
+            rt, ri, rj = ref.log()
+            _, (t, i, j) = bld.evolve_events(k, log_capacity=k)
+            assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+            assert_bits_equal(t, rt, "event times")
+
+        def same_tables():
+            assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
+            bt, bi, ot, oo, _ = ref.minima()
+            assert_bits_equal(bld._balls_toi, bt)
+            assert [int(x) for x in bld._balls_idx] == bi.tolist()
+            assert_bits_equal(bld._obstacles_toi, ot)
+
+        step(n1)
+        # in-place velocity edit of one ball + recompute_toi(index), simulation.py:226-309
+        v = bld.balls_velocity[5].copy()
+        bld.balls_velocity[5] = (-v[1], v[0])
+        bld.recompute_toi(5)
+        ref.set_ball(5, vel=(-v[1], v[0]))
+        ref.recompute_toi(5)
+        same_tables()
+        step(n1)
+        # a new ball in the middle of a run (no table sync in between: add_ball must do it)
+        side = float(n_side)
+        bld.add_ball((side / 2 + 0.013, side / 2 + 0.021), (0.3, -0.4), radius=0.0, mass=2.0)
+        ref.add_ball((side / 2 + 0.013, side / 2 + 0.021), (0.3, -0.4), radius=0.0, mass=2.0)
+        step(n1)
+        same_tables()
+        # recompute everything, then go on
+        bld.recompute_toi()
+        ref.recompute_toi()
+        same_tables()
+        step(n1)
+        assert_bits_equal(bld.balls_velocity, ref.state()["v"])
+        assert_bits_equal(bld.balls_initial_position, ref.state()["p0"])
+    finally:
+        h.check(h.lib.bl_set_small_kernel(h.h, 1))
+
+
 def test_cradle_nudge(billiards, golden):
     g = golden("cradle")
     b = build(billiards, workloads.newtons_cradle(5, True), bool(g["dot_fma"]), one_by_one=True)
