@@ -14,6 +14,8 @@
  *   toi_ball_ball            physics.py:33-76
  *   elastic_collision        physics.py:273-282
  *   InfiniteWall.detect/resolve  obstacles.py:112-144
+ *   LineSegment.detect/resolve   obstacles.py:172-198, physics.toi_ball_point :79-144,
+ *                                physics.toi_and_param_ball_segment :147-252
  *   Disk.detect/resolve      obstacles.py:70-76
  *   Billiard.add_ball        simulation.py:141-224
  *   Billiard.recompute_toi   simulation.py:226-309
@@ -41,6 +43,7 @@
 #define ORC_INF (INFINITY)
 #define ORC_OBS_WALL 0
 #define ORC_OBS_DISK 1
+#define ORC_OBS_SEGMENT 2
 
 #define ORC_OK 0
 #define ORC_ESEPARATING (-3) /* physics.py:277-279 ValueError */
@@ -51,7 +54,8 @@
 
 typedef struct {
     int kind;
-    double a, b, c, d; /* wall: start x,y, normal x,y ; disk: centre x,y, radius, unused */
+    double a, b, c, d; /* wall: start x,y, normal x,y ; disk: centre x,y, radius, unused ; segment: start, covector */
+    double e, f, g, h; /* segment: unit normal x,y, end point x,y (obstacles.py:150-170) */
 } orc_obstacle;
 
 typedef struct {
@@ -123,7 +127,44 @@ static int elastic_collision(orc_billiard *o, const double *p1, const double *v1
     return ORC_OK;
 }
 
-/* obstacles.py:112-133 (wall) and :70-72 (disk); returns relative time, *arg = headway */
+/* physics.py:100-144: a moving ball against a static point */
+static double toi_ball_point(orc_billiard *o, const double *pos, const double *vel, double radius, double qx, double qy,
+                             double t_eps) {
+    double dpx = pos[0] - qx, dpy = pos[1] - qy;
+    double b = dot2(o, dpx, dpy, vel[0], vel[1]);
+    if (b >= 0) return ORC_INF;
+    double dist = dot2(o, dpx, dpy, dpx, dpy);
+    double speed = dot2(o, vel[0], vel[1], vel[0], vel[1]);
+    double c = dist - pow2(radius);
+    double disc = b * b - speed * c;
+    if (disc <= 0) return ORC_INF;
+    double t1 = c / (-b + sqrt(disc));
+    return t1 >= t_eps ? t1 : ORC_INF;
+}
+
+/* physics.py:213-252: a moving ball against an open segment; *code = 0: *u is the line parameter of the hit,
+ * 1: "try the start point", 2: "try the end point", 3: None */
+static double toi_param_ball_segment(orc_billiard *o, const double *pos, const double *vel, double radius,
+                                     const orc_obstacle *sg, double t_eps, double *u, int *code) {
+    double dpx = (pos[0] - sg->a) + t_eps * vel[0], dpy = (pos[1] - sg->b) + t_eps * vel[1];
+    double dl = dot2(o, sg->c, sg->d, dpx, dpy);
+    double dn = dot2(o, sg->e, sg->f, dpx, dpy);
+    *u = 0.0;
+    if (fabs(dn) <= radius) {
+        *code = dl < 0 ? 1 : (dl > 1 ? 2 : 3);
+        return ORC_INF;
+    }
+    double vn = dot2(o, sg->e, sg->f, vel[0], vel[1]);
+    if (vn == 0) { *code = 3; return ORC_INF; }
+    double t = -(dn + (dn > 0 ? -radius : radius)) / vn;
+    if (t < 0) { *code = 3; return ORC_INF; }
+    double uu = dl + t * dot2(o, sg->c, sg->d, vel[0], vel[1]);
+    if (0 <= uu && uu <= 1) { *u = uu; *code = 0; return t + t_eps; }
+    *code = uu < 0 ? 1 : 2;
+    return ORC_INF;
+}
+
+/* obstacles.py:112-133 (wall), :70-72 (disk), :172-183 (segment); returns relative time, *arg = headway / u */
 static double obstacle_detect(orc_billiard *o, const orc_obstacle *ob, const double *pos, const double *vel,
                               double radius, double *arg) {
     *arg = 0.0;
@@ -134,6 +175,18 @@ static double obstacle_detect(orc_billiard *o, const orc_obstacle *ob, const dou
         double t = gap / headway;
         if (t < -1e-10) return ORC_INF;
         *arg = headway;
+        return t;
+    }
+    if (ob->kind == ORC_OBS_SEGMENT) {
+        double u;
+        int code;
+        double t = toi_param_ball_segment(o, pos, vel, radius, ob, -1e-10, &u, &code);
+        if (isinf(t)) {
+            if (code == 1) { *arg = 0.0; return toi_ball_point(o, pos, vel, radius, ob->a, ob->b, -1e-10); }
+            if (code == 2) { *arg = 1.0; return toi_ball_point(o, pos, vel, radius, ob->g, ob->h, -1e-10); }
+            return t;
+        }
+        *arg = u;
         return t;
     }
     /* Disk: toi_ball_ball(center, (0,0), R, pos, vel, radius) */
@@ -149,6 +202,15 @@ static int obstacle_resolve(orc_billiard *o, const orc_obstacle *ob, const doubl
         return ORC_OK;
     }
     double c[2] = {ob->a, ob->b}, z[2] = {0.0, 0.0}, w1[2];
+    if (ob->kind == ORC_OBS_SEGMENT) {
+        /* obstacles.py:185-198: u == 0 / u == 1 -> elastic collision with that end point, else mirror at the line */
+        if (arg == 0.0) return elastic_collision(o, c, z, 1.0, pos, vel, 0.0, w1, w);
+        if (arg == 1.0) { c[0] = ob->g; c[1] = ob->h; return elastic_collision(o, c, z, 1.0, pos, vel, 0.0, w1, w); }
+        double d2 = 2 * dot2(o, ob->e, ob->f, vel[0], vel[1]);
+        w[0] = vel[0] - d2 * ob->e;
+        w[1] = vel[1] - d2 * ob->f;
+        return ORC_OK;
+    }
     return elastic_collision(o, c, z, 1.0, pos, vel, 0.0, w1, w);
 }
 
@@ -172,13 +234,26 @@ void orc_destroy(orc_billiard *o) {
     free(o);
 }
 
+static int add_obstacle8(orc_billiard *o, orc_obstacle ob) {
+    if (o->n > 0) return ORC_EINVAL; /* obstacles are fixed at construction, simulation.py:96-103 */
+    if (o->nobs == o->obs_cap) {
+        o->obs_cap = o->obs_cap ? 2 * o->obs_cap : 8;
+        o->obs = (orc_obstacle *)realloc(o->obs, sizeof(orc_obstacle) * o->obs_cap);
+    }
+    o->obs[o->nobs] = ob;
+    return o->nobs++;
+}
+int orc_add_segment(orc_billiard *o, const double *sg /* start, covector, normal, end */) {
+    orc_obstacle ob = {ORC_OBS_SEGMENT, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], sg[6], sg[7]};
+    return add_obstacle8(o, ob);
+}
 static int add_obstacle(orc_billiard *o, int kind, double a, double b, double c, double d) {
     if (o->n > 0) return ORC_EINVAL; /* obstacles are fixed at construction, simulation.py:96-103 */
     if (o->nobs == o->obs_cap) {
         o->obs_cap = o->obs_cap ? 2 * o->obs_cap : 8;
         o->obs = (orc_obstacle *)realloc(o->obs, sizeof(orc_obstacle) * o->obs_cap);
     }
-    orc_obstacle ob = {kind, a, b, c, d};
+    orc_obstacle ob = {kind, a, b, c, d, 0.0, 0.0, 0.0, 0.0};
     o->obs[o->nobs] = ob;
     return o->nobs++;
 }
@@ -510,15 +585,38 @@ int orc_elastic_collision(int dot_fma, const double *p1, const double *v1, doubl
 double orc_wall_detect(int dot_fma, const double *wall /* sx,sy,nx,ny */, const double *pos, const double *vel,
                        double radius, double *headway) {
     orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
-    orc_obstacle ob = {ORC_OBS_WALL, wall[0], wall[1], wall[2], wall[3]};
+    orc_obstacle ob = {ORC_OBS_WALL, wall[0], wall[1], wall[2], wall[3], 0.0, 0.0, 0.0, 0.0};
     return obstacle_detect(&o, &ob, pos, vel, radius, headway);
 }
 double orc_disk_detect(int dot_fma, const double *disk /* cx,cy,R */, const double *pos, const double *vel,
                        double radius) {
     orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
-    orc_obstacle ob = {ORC_OBS_DISK, disk[0], disk[1], disk[2], 0.0};
+    orc_obstacle ob = {ORC_OBS_DISK, disk[0], disk[1], disk[2], 0.0, 0.0, 0.0, 0.0, 0.0};
     double arg;
     return obstacle_detect(&o, &ob, pos, vel, radius, &arg);
+}
+
+double orc_toi_ball_point(int dot_fma, const double *pos, const double *vel, double radius, const double *point,
+                          double t_eps) {
+    orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
+    return toi_ball_point(&o, pos, vel, radius, point[0], point[1], t_eps);
+}
+double orc_segment_param(int dot_fma, const double *sg /* start, covector, normal, end */, const double *pos,
+                         const double *vel, double radius, double t_eps, double *u, int *code) {
+    orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
+    orc_obstacle ob = {ORC_OBS_SEGMENT, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], sg[6], sg[7]};
+    return toi_param_ball_segment(&o, pos, vel, radius, &ob, t_eps, u, code);
+}
+double orc_segment_detect(int dot_fma, const double *sg, const double *pos, const double *vel, double radius,
+                          double *arg) {
+    orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
+    orc_obstacle ob = {ORC_OBS_SEGMENT, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], sg[6], sg[7]};
+    return obstacle_detect(&o, &ob, pos, vel, radius, arg);
+}
+int orc_segment_resolve(int dot_fma, const double *sg, const double *pos, const double *vel, double arg, double *w) {
+    orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
+    orc_obstacle ob = {ORC_OBS_SEGMENT, sg[0], sg[1], sg[2], sg[3], sg[4], sg[5], sg[6], sg[7]};
+    return obstacle_resolve(&o, &ob, pos, vel, arg, w);
 }
 
 /* ---------------------------------------------------------------- single-particle ensemble (config S)

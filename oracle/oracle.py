@@ -27,7 +27,8 @@ ORC_EDIVZERO = -4
 
 class _Obstacle(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("a", ctypes.c_double), ("b", ctypes.c_double),
-                ("c", ctypes.c_double), ("d", ctypes.c_double)]
+                ("c", ctypes.c_double), ("d", ctypes.c_double), ("e", ctypes.c_double), ("f", ctypes.c_double),
+                ("g", ctypes.c_double), ("h", ctypes.c_double)]
 
 
 def build(force=False):
@@ -52,6 +53,15 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_add_wall.argtypes = [vp] + [ctypes.c_double] * 4
         L.orc_add_disk.argtypes = [vp] + [ctypes.c_double] * 3
+        L.orc_add_segment.argtypes = [vp, dp]
+        L.orc_toi_ball_point.restype = ctypes.c_double
+        L.orc_toi_ball_point.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, dp, ctypes.c_double]
+        L.orc_segment_param.restype = ctypes.c_double
+        L.orc_segment_param.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_double, dp,
+                                        ctypes.POINTER(ctypes.c_int)]
+        L.orc_segment_detect.restype = ctypes.c_double
+        L.orc_segment_detect.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, dp]
+        L.orc_segment_resolve.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, dp]
         L.orc_add_ball.argtypes = [vp] + [ctypes.c_double] * 6
         L.orc_enable_log.argtypes = [vp, ctypes.c_longlong, ctypes.c_int]
         L.orc_bounce_ball_ball.argtypes = [vp]
@@ -119,6 +129,9 @@ class OracleBilliard:
                 self._L.orc_add_wall(self._h, float(ob[1][0]), float(ob[1][1]), float(ob[2][0]), float(ob[2][1]))
             elif ob[0] == "disk":
                 self._L.orc_add_disk(self._h, float(ob[1][0]), float(ob[1][1]), float(ob[2]))
+            elif ob[0] == "segment":  # ("segment", start, covector, normal, end), all pairs of floats
+                sg = _f64([x for pair in ob[1:5] for x in pair], 8)
+                self._L.orc_add_segment(self._h, _dp(sg))
             else:
                 raise ValueError(ob)
 
@@ -310,6 +323,44 @@ def disk_detect(center, R, pos, vel, radius, dot_fma=True):
     return lib().orc_disk_detect(int(bool(dot_fma)), _dp(d), _dp(_f64(pos, 2)), _dp(_f64(vel, 2)), float(radius))
 
 
+def toi_ball_point(pos, vel, radius, point, t_eps=-1e-10, dot_fma=True):
+    """physics.toi_ball_point (physics.py:79-144)"""
+    return lib().orc_toi_ball_point(int(bool(dot_fma)), _dp(_f64(pos, 2)), _dp(_f64(vel, 2)), float(radius),
+                                    _dp(_f64(point, 2)), float(t_eps))
+
+
+def _segment8(segment):
+    """("segment", start, covector, normal, end) or the four pairs -> 8 doubles"""
+    parts = segment[1:5] if segment[0] == "segment" else segment
+    return _f64([x for pair in parts for x in pair], 8)
+
+
+def segment_param(segment, pos, vel, radius, t_eps=-1e-10, dot_fma=True):
+    """physics.toi_and_param_ball_segment (physics.py:147-252) -> (t, u) with u a float, 0, 1 or None"""
+    u, code = ctypes.c_double(), ctypes.c_int()
+    t = lib().orc_segment_param(int(bool(dot_fma)), _dp(_segment8(segment)), _dp(_f64(pos, 2)), _dp(_f64(vel, 2)),
+                                float(radius), float(t_eps), ctypes.byref(u), ctypes.byref(code))
+    return t, (u.value if code.value == 0 else 0 if code.value == 1 else 1 if code.value == 2 else None)
+
+
+def segment_detect(segment, pos, vel, radius, dot_fma=True):
+    """LineSegment.detect_collision (obstacles.py:172-183) -> (t, u)"""
+    arg = ctypes.c_double()
+    t = lib().orc_segment_detect(int(bool(dot_fma)), _dp(_segment8(segment)), _dp(_f64(pos, 2)), _dp(_f64(vel, 2)),
+                                 float(radius), ctypes.byref(arg))
+    return t, arg.value
+
+
+def segment_resolve(segment, pos, vel, u, dot_fma=True):
+    """LineSegment.resolve_collision (obstacles.py:185-198)"""
+    w = np.empty(2)
+    st = lib().orc_segment_resolve(int(bool(dot_fma)), _dp(_segment8(segment)), _dp(_f64(pos, 2)), _dp(_f64(vel, 2)),
+                                   float(u), _dp(w))
+    if st:
+        raise OracleError(st)
+    return w
+
+
 def ensemble_run(obstacles, pos, vel, n_collisions, radius=0.0, dot_fma=True, count_hits=False):
     """Config S: every system = one ball + the shared obstacles; n_collisions x bounce_ball_obstacle()."""
     pos = np.asarray(pos, dtype=np.float64)
@@ -318,9 +369,11 @@ def ensemble_run(obstacles, pos, vel, n_collisions, radius=0.0, dot_fma=True, co
     obs = (_Obstacle * max(len(obstacles), 1))()
     for q, ob in enumerate(obstacles):
         if ob[0] == "wall":
-            obs[q] = _Obstacle(0, float(ob[1][0]), float(ob[1][1]), float(ob[2][0]), float(ob[2][1]))
+            obs[q] = _Obstacle(0, float(ob[1][0]), float(ob[1][1]), float(ob[2][0]), float(ob[2][1]), 0.0, 0.0, 0.0, 0.0)
+        elif ob[0] == "segment":
+            obs[q] = _Obstacle(2, *[float(x) for pair in ob[1:5] for x in pair])
         else:
-            obs[q] = _Obstacle(1, float(ob[1][0]), float(ob[1][1]), float(ob[2]), 0.0)
+            obs[q] = _Obstacle(1, float(ob[1][0]), float(ob[1][1]), float(ob[2]), 0.0, 0.0, 0.0, 0.0, 0.0)
     state = np.ascontiguousarray(np.concatenate([pos, vel], axis=1))
     t_out = np.empty(n_sys)
     done = np.zeros(n_sys, dtype=np.int64)

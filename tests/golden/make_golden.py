@@ -347,6 +347,70 @@ def main():
              disk=np.asarray([0.3, -0.2, 0.75]), wp=wp, wv=wv, wr=wr, wall_t=wt, wall_headway=wh, wall_res=wres,
              disk_t=dtm, disk_res=dres, disk_sep=dsep)
 
+    # ---- M: LineSegment obstacles (examples/maze.py) and the segment / point kernels -------------------
+    if want("maze"):
+        logged_case(ref, dot_fma, workloads.maze(), "maze", n_events=3000, payload=True)
+        logged_case(ref, dot_fma, workloads.maze_wide(), "maze_wide", n_events=4000, payload=True)
+
+    if want("segment"):
+        import importlib
+        rp = importlib.import_module("billiards_ref.physics")
+        ro = importlib.import_module("billiards_ref.obstacles")
+        rng = np.random.default_rng(2024)
+        n = 3000
+        seg_pts = [((-0.3, -1.0), (-0.3, 0.5)), ((-0.2, -0.4), (0.2, 0.4)), ((1.25, 0.5), (-0.75, 2.0)), ((0, 0), (2, 0))]
+        which = rng.integers(0, len(seg_pts), n)
+        pos = rng.uniform(-2.5, 2.5, (n, 2))
+        vel = rng.standard_normal((n, 2))
+        rad = rng.uniform(0, 0.3, n)
+        rad[::5] = 0.0
+        # aim a third of the balls at the segment they are tested against, another part at its end points
+        segs = [ro.LineSegment(a, b) for a, b in seg_pts]
+        for k in range(n):
+            a, b = np.asarray(seg_pts[which[k]], dtype=np.float64)
+            if k % 3 == 0:
+                target = a + rng.uniform(-0.1, 1.1) * (b - a)
+                vel[k] = (target - pos[k]) * rng.uniform(0.3, 2.0)
+            elif k % 3 == 1:
+                target = (a if rng.random() < 0.5 else b) + 0.5 * rad[k] * rng.standard_normal(2)
+                vel[k] = (target - pos[k]) * rng.uniform(0.3, 2.0)
+        vel[7] = (0.0, 0.0)
+        vel[8] = (1.0, 0.0)       # parallel to the last segment
+        which[8] = 3
+        pos[8] = (-1.0, 0.7)
+        ok = np.asarray([x ** 2 == x * x for x in rad.tolist()])
+        rad[~ok] = 0.125
+        seg8 = np.zeros((n, 8))
+        pt_t = np.zeros(n); par_t = np.zeros(n); par_u = np.zeros(n); par_code = np.zeros(n, dtype=np.int64)
+        det_t = np.zeros(n); det_u = np.full(n, np.nan); det_code = np.zeros(n, dtype=np.int64)
+        res = np.zeros((n, 2)); res0 = np.zeros((n, 2)); res1 = np.zeros((n, 2)); sep = np.zeros((n, 3), dtype=np.int64)
+        for k in range(n):
+            sg = segs[which[k]]
+            seg8[k] = [sg.start_point[0], sg.start_point[1], sg._covector[0], sg._covector[1], sg._normal[0],
+                       sg._normal[1], sg.end_point[0], sg.end_point[1]]
+            pt_t[k] = rp.toi_ball_point(pos[k], vel[k], float(rad[k]), sg.end_point) if vel[k].any() else np.inf
+            t, u = rp.toi_and_param_ball_segment(pos[k], vel[k], float(rad[k]), sg.start_point, sg._covector, sg._normal)
+            par_t[k] = t
+            par_code[k] = 3 if u is None else (0 if isinstance(u, float) else 1 + int(u))
+            par_u[k] = float(u) if isinstance(u, float) else 0.0
+            if vel[k].any():
+                t, (u,) = sg.detect_collision(pos[k], vel[k], float(rad[k]))
+            else:
+                t, u = np.inf, None
+            det_t[k] = t
+            det_code[k] = 3 if u is None else (0 if isinstance(u, float) else 1 + int(u))
+            det_u[k] = np.nan if u is None else float(u)
+            for col, uu, out in ((0, 0.37, res), (1, 0, res0), (2, 1, res1)):
+                try:
+                    out[k] = sg.resolve_collision(pos[k], vel[k], float(rad[k]), uu)
+                except ValueError:
+                    sep[k, col] = 1
+        print(f"segment: finite detect share {np.isfinite(det_t).mean():.3f}, face hits {(det_code == 0).mean():.3f}, "
+              f"end-point tries {((det_code == 1) | (det_code == 2)).mean():.3f}")
+        save("segment_vectors", dot_fma=np.int64(dot_fma), seg=seg8, pos=pos, vel=vel, rad=rad, point_t=pt_t,
+             param_t=par_t, param_u=par_u, param_code=par_code, detect_t=det_t, detect_u=det_u, detect_code=det_code,
+             resolve_face=res, resolve_start=res0, resolve_end=res1, resolve_sep=sep)
+
 
 if __name__ == "__main__":
     main()

@@ -26,6 +26,8 @@ LOGGED = [
     ("dense_gas_256", lambda: workloads.dense_gas(16), dict(n_events=2000)),
     ("dense_gas_1024", lambda: workloads.dense_gas(32), dict(n_events=1000)),
     ("ideal_gas_1024", lambda: workloads.ideal_gas(32), dict(n_events=1000)),
+    ("maze", workloads.maze, dict(n_events=3000)),            # LineSegment obstacles, examples/maze.py
+    ("maze_wide", workloads.maze_wide, dict(n_events=4000)),  # all four segments, both faces, end points
 ]
 
 
@@ -233,6 +235,48 @@ def test_unit_vectors(oracle, golden):
     assert_bits_equal(wt, g["wall_t"], "wall toi")
     assert_bits_equal(wh, g["wall_headway"], "wall headway")
     assert_bits_equal(dt, g["disk_t"], "disk toi")
+
+
+def test_segment_vectors(oracle, golden):
+    """physics.toi_ball_point, physics.toi_and_param_ball_segment, LineSegment.detect/resolve_collision of the live
+    reference on 3000 random inputs (a third aimed at the segment, a third at its end points)."""
+    g = golden("segment_vectors")
+    fma = bool(g["dot_fma"])
+    for k in range(len(g["rad"])):
+        row = g["seg"][k]
+        seg = [tuple(row[0:2]), tuple(row[2:4]), tuple(row[4:6]), tuple(row[6:8])]
+        pos, vel, rad = g["pos"][k], g["vel"][k], float(g["rad"][k])
+        moving = bool(vel.any())
+        if moving:
+            assert oracle.toi_ball_point(pos, vel, rad, seg[3], dot_fma=fma) == g["point_t"][k], k
+        t, u = oracle.segment_param(seg, pos, vel, rad, dot_fma=fma)
+        code = 3 if u is None else (0 if isinstance(u, float) else 1 + u)
+        assert (t, code) == (g["param_t"][k], int(g["param_code"][k])), k
+        if code == 0:
+            assert u == g["param_u"][k], k
+        if moving:
+            t, u = oracle.segment_detect(seg, pos, vel, rad, dot_fma=fma)
+            assert t == g["detect_t"][k], k
+            if np.isfinite(t):
+                assert u == g["detect_u"][k], k
+        for col, uu, key in ((0, 0.37, "resolve_face"), (1, 0, "resolve_start"), (2, 1, "resolve_end")):
+            try:
+                w = oracle.segment_resolve(seg, pos, vel, uu, dot_fma=fma)
+                assert not g["resolve_sep"][k, col], k
+                assert_bits_equal(w, g[key][k], f"{key}[{k}]")
+            except oracle.OracleError:
+                assert g["resolve_sep"][k, col], k
+
+
+def test_maze_payload(oracle, golden):
+    g = golden("maze_wide")
+    o = workloads.maze_wide().build_oracle(oracle, dot_fma=bool(g["dot_fma"]))
+    o.enable_log(4000, payload=True)
+    o.evolve(float("inf"), max_events=4000)
+    t, i, j, p = o.log(payload=True)
+    assert_bits_equal(p, g["log_payload"], "callback payloads (position, velocities, line parameter u)")
+    seg = j <= -5
+    assert int(((p[seg, 6] == 0) | (p[seg, 6] == 1)).sum()) >= 30   # end-point hits are in the fixture
 
 
 def test_known_answers(oracle):

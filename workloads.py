@@ -8,7 +8,7 @@ Config letters follow SURVEY.md: G Galperin, P pool first shot, I ideal gas, D d
 S Sinai ensemble, H heterogeneous gas (parity stress), C Newton's cradle.
 """
 
-from math import pi, sqrt
+from math import cos, pi, sin, sqrt
 
 import numpy as np
 
@@ -51,9 +51,23 @@ def oracle_obstacles(obstacles):
         if ob[0] == "wall":
             n = wall_normal(ob[1], ob[2], ob[3])
             out.append(("wall", (float(ob[1][0]), float(ob[1][1])), (float(n[0]), float(n[1]))))
+        elif ob[0] == "segment":
+            out.append(segment_record(ob[1], ob[2]))
         else:
             out.append(("disk", (float(ob[1][0]), float(ob[1][1])), ob[2]))
     return out
+
+
+def segment_record(start, end):
+    """("segment", start, covector, normal, end) with the numbers LineSegment.__init__ derives
+    (obstacles.py:159-170: direction / |direction|^2 and the left-hand unit normal), computed with numpy like there"""
+    start, end = np.asarray(start), np.asarray(end)
+    direction = end - start
+    length_sqrd = direction.dot(direction)
+    covector = direction / length_sqrd
+    normal = np.array([-direction[1], direction[0]]) / sqrt(length_sqrd)
+    return ("segment", (float(start[0]), float(start[1])), (float(covector[0]), float(covector[1])),
+            (float(normal[0]), float(normal[1])), (float(end[0]), float(end[1])))
 
 
 def make_obstacles(mod, obstacles):
@@ -62,6 +76,8 @@ def make_obstacles(mod, obstacles):
     for ob in obstacles:
         if ob[0] == "wall":
             out.append(mod.InfiniteWall(ob[1], ob[2], ob[3]))
+        elif ob[0] == "segment":
+            out.append(mod.LineSegment(ob[1], ob[2]))
         else:
             out.append(mod.Disk(ob[1], ob[2]))
     return out
@@ -193,6 +209,43 @@ def sinai(n_systems, seed=0, speed=1.0):
     theta = rng.uniform(0.0, 2.0 * pi, n_systems)
     vel = speed * np.stack([np.cos(theta), np.sin(theta)], axis=1)
     return SINAI_OBSTACLES, pos, vel
+
+
+MAZE_OBSTACLES = box_walls(-1, -1, 1, 1) + [
+    ("segment", (-0.3, -1), (-0.3, 0.5)), ("segment", (0.3, 1), (0.3, -0.5)),
+    ("segment", (-0.2, -0.4), (0.2, 0.4)), ("segment", (-0.2, 0.4), (0.2, -0.4)),
+]
+
+
+def maze(num_balls=200, radius=0.02):
+    """Config M: examples/maze.py:17-43 -- an ideal gas released in one corner of a box with four LineSegments."""
+    rs = np.random.RandomState(1)  # the example calls np.random.seed(1)
+    pos, vel = [], []
+    for _ in range(num_balls):
+        pos.append(rs.uniform((-0.98, -0.98), (-0.32, -0.32)))
+        angle = rs.uniform(0, 2 * pi)
+        vel.append(np.asarray([cos(angle), sin(angle)]) / 2)
+    return Config("maze", MAZE_OBSTACLES, pos, vel, radius, 1.0)
+
+
+def maze_wide(num_balls=150, radius=0.02, seed=7):
+    """Config M2: the maze of examples/maze.py with the gas spread over the whole box, so that all four segments,
+    both of their faces and their end points get hit within a few thousand collisions."""
+    rng = np.random.default_rng(seed)
+    segs = [(np.asarray(ob[1], dtype=np.float64), np.asarray(ob[2], dtype=np.float64)) for ob in MAZE_OBSTACLES
+            if ob[0] == "segment"]
+    pos = []
+    while len(pos) < num_balls:
+        p = rng.uniform(-0.95, 0.95, 2)
+        ok = all(np.hypot(*(p - q)) > 2.5 * radius for q in pos)
+        for a, b in segs:
+            u = min(1.0, max(0.0, float((p - a).dot(b - a) / (b - a).dot(b - a))))
+            ok = ok and np.hypot(*(p - (a + u * (b - a)))) > 2.5 * radius
+        if ok:
+            pos.append(p)
+    theta = rng.uniform(0, 2 * pi, num_balls)
+    vel = np.stack([np.cos(theta), np.sin(theta)], axis=1) / 2
+    return Config("maze_wide", MAZE_OBSTACLES, pos, vel, radius, 1.0)
 
 
 def newtons_cradle(num_balls=5, with_walls=True):
