@@ -18,7 +18,7 @@ BL_OK = 0
 BL_ECUDA, BL_EINVAL, BL_ESEPARATING, BL_EDIVZERO, BL_ENAN, BL_EUNSUPPORTED, BL_EASSERT = -1, -2, -3, -4, -5, -6, -7
 BL_STOP_TIME, BL_STOP_EVENTS, BL_STOP_LOG, BL_STOP_ERROR = 0, 1, 2, 3
 BL_ANY, BL_BALL_BALL, BL_BALL_OBSTACLE = 0, 1, 2
-BL_OBS_WALL, BL_OBS_DISK = 0, 1
+BL_OBS_WALL, BL_OBS_DISK, BL_OBS_SEGMENT = 0, 1, 2
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_void = ctypes.c_void_p
@@ -26,7 +26,8 @@ c_void = ctypes.c_void_p
 
 class BlObstacle(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("pad", ctypes.c_int32), ("a", ctypes.c_double), ("b", ctypes.c_double),
-                ("c", ctypes.c_double), ("d", ctypes.c_double)]
+                ("c", ctypes.c_double), ("d", ctypes.c_double), ("e", ctypes.c_double), ("f", ctypes.c_double),
+                ("g", ctypes.c_double), ("h", ctypes.c_double)]
 
 
 class BlSystem(ctypes.Structure):
@@ -76,6 +77,9 @@ SIGNATURES = {
                                           ctypes.c_int64, c_void]),
     "bl_obstacle_resolve": (ctypes.c_int, [_H, ctypes.POINTER(BlObstacle), c_void, c_void, c_void, c_void,
                                            ctypes.c_int64, c_void]),
+    "bl_toi_ball_point": (ctypes.c_int, [_H, c_void, c_void, ctypes.c_double, c_void, ctypes.c_int64, c_void]),
+    "bl_toi_and_param_ball_segment": (ctypes.c_int, [_H, ctypes.POINTER(BlObstacle), c_void, ctypes.c_double, c_void,
+                                                     c_void, c_void, ctypes.c_int64, c_void]),
     "bl_ensemble_run": (ctypes.c_int, [_H, ctypes.POINTER(BlObstacle), ctypes.c_int, c_double_p, ctypes.c_double,
                                        ctypes.c_int64, c_void, c_void, ctypes.c_int64, ctypes.c_double, c_void, c_void,
                                        c_void, c_void]),

@@ -46,7 +46,8 @@ class BilliardEnsemble:
         self._rec_array = (_lib.BlObstacle * max(len(self._records), 1))(*self._records)
         self.radius = float(radius)
         # (R + r)**2 with Python floats, like Disk.detect_collision -> toi_ball_ball does (physics.py:52)
-        self._rsum2 = np.asarray([float((o.radius + self.radius) ** 2) if r.kind == _lib.BL_OBS_DISK else 0.0
+        self._rsum2 = np.asarray([float((o.radius + self.radius) ** 2) if r.kind == _lib.BL_OBS_DISK else
+                                  float(self.radius ** 2) if r.kind == _lib.BL_OBS_SEGMENT else 0.0
                                   for o, r in zip(self.obstacles, self._records)] or [0.0], dtype=np.float64)
         # numpy arrays or (pinned) torch CPU tensors of shape (n, 2); the H2D copy is asynchronous for pinned input
         pos_t = pos if isinstance(pos, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))

@@ -6,6 +6,8 @@
 ``bl_obstacle_resolve``), one problem per call.
 """
 
+from math import sqrt
+
 import numpy as np
 
 from . import _lib
@@ -118,15 +120,37 @@ class InfiniteWall(Obstacle):
 
 
 class LineSegment(Obstacle):
-    """Two-sided segment with rounded ends (obstacles.py:147-198) -- NOT on the B200 hot path yet.
-
-    The constructor validates like the reference; using the segment in a ``Billiard`` raises NotImplementedError
-    (north-star scope is InfiniteWall and Disk; SURVEY.md 8f3 lists this as the next obstacle kind).
-    """
+    """A line segment that balls bounce off from both sides and from its two end points (obstacles.py:147-198)."""
 
     def __init__(self, start_point, end_point):
         self.start_point = np.asarray(start_point)
         self.end_point = np.asarray(end_point)
         direction = self.end_point - self.start_point
-        if direction[0] == 0.0 and direction[1] == 0.0:
+        length_sqrd = direction.dot(direction)
+        if length_sqrd == 0.0:
             raise ValueError("this is not a line")
+        # the two derived vectors feed the kernels, so they are formed with the same numpy operations as in the
+        # reference's constructor: direction / |direction|^2 and the left-hand normal / |direction|
+        self._covector = direction / length_sqrd
+        self._normal = np.array([-direction[1], direction[0]]) / sqrt(length_sqrd)
+
+    def _device_record(self):
+        return _lib.BlObstacle(_lib.BL_OBS_SEGMENT, 0, float(self.start_point[0]), float(self.start_point[1]),
+                               float(self._covector[0]), float(self._covector[1]), float(self._normal[0]),
+                               float(self._normal[1]), float(self.end_point[0]), float(self.end_point[1]))
+
+    @staticmethod
+    def _args(u):
+        """the args tuple of the reference: (0,) / (1,) for the end points, (float u,) for the line part"""
+        return (int(u),) if u in (0.0, 1.0) else (np.float64(u),)
+
+    def detect_collision(self, pos, vel, radius):
+        """Time until the ball touches the segment or one of its end points, and where: (t, (u,))."""
+        t, u = self._detect_on_device(pos, vel, radius, radius ** 2)
+        if t == INF:
+            return INF, (None,)
+        return t, self._args(u)
+
+    def resolve_collision(self, pos, vel, radius, u):
+        """Velocity after the bounce: elastic collision with an end point for u = 0 / 1, mirror image otherwise."""
+        return self._resolve_on_device(pos, vel, radius, float(u))

@@ -95,10 +95,35 @@ def elastic_collision(pos1, vel1, mass1, pos2, vel2, mass2):
     return w1[0], w2[0]
 
 
-def toi_ball_point(*args, **kwargs):
-    raise NotImplementedError("toi_ball_point (LineSegment support) is not on the B200 hot path yet (SURVEY.md 8f3)")
+def toi_ball_point(pos, vel, radius, point, t_eps=-1e-10):
+    """Time of impact of a moving ball and a static point, infinite if there is none (physics.py:79-144)."""
+    import torch
+    h = _lib.get_handle()
+    p, v, q = _vec2(pos, "pos"), _vec2(vel, "vel"), _vec2(point, "point")
+    d_in = torch.from_numpy(np.concatenate([p, v, q])).to(h.torch_device)
+    d_r2 = torch.tensor([float(radius ** 2)], dtype=torch.float64, device=h.torch_device)  # physics.py:120
+    d_out = torch.empty(1, dtype=torch.float64, device=h.torch_device)
+    h.check(h.lib.bl_toi_ball_point(h.h, _lib.ptr(d_in), _lib.ptr(d_r2), float(t_eps), _lib.ptr(d_out), 1, h.stream()))
+    return float(d_out.item())
 
 
-def toi_and_param_ball_segment(*args, **kwargs):
-    raise NotImplementedError(
-        "toi_and_param_ball_segment (LineSegment support) is not on the B200 hot path yet (SURVEY.md 8f3)")
+def toi_and_param_ball_segment(pos, vel, radius, line_start, covector, normal, t_eps=-1e-10):
+    """Time of impact of a moving ball and an open line segment, with the line parameter of the hit
+    (physics.py:147-252).
+
+    Returns ``(t, u)``: ``t`` finite and ``u`` in [0, 1] for a hit on the segment; ``(inf, 0)`` / ``(inf, 1)`` when
+    only the start / end point can still be hit (test it with ``toi_ball_point``); ``(inf, None)`` otherwise.
+    """
+    import torch
+    h = _lib.get_handle()
+    p, v = _vec2(pos, "pos"), _vec2(vel, "vel")
+    s0, cv, nm = _vec2(line_start, "line_start"), _vec2(covector, "covector"), _vec2(normal, "normal")
+    rec = _lib.BlObstacle(_lib.BL_OBS_SEGMENT, 0, s0[0], s0[1], cv[0], cv[1], nm[0], nm[1], 0.0, 0.0)
+    d_in = torch.from_numpy(np.concatenate([p, v, [float(radius)]])).to(h.torch_device)
+    d_out = torch.empty(2, dtype=torch.float64, device=h.torch_device)
+    d_code = torch.empty(1, dtype=torch.int32, device=h.torch_device)
+    h.check(h.lib.bl_toi_and_param_ball_segment(h.h, rec, _lib.ptr(d_in), float(t_eps), _lib.ptr(d_out[:1]),
+                                                _lib.ptr(d_out[1:]), _lib.ptr(d_code), 1, h.stream()))
+    t, u = d_out.cpu().tolist()
+    code = int(d_code.item())
+    return t, (np.float64(u) if code == 0 else 0 if code == 1 else 1 if code == 2 else None)

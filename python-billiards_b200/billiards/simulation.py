@@ -154,11 +154,12 @@ class Billiard:
                 grew = True
         dev = h.torch_device
         if grew or "rsum2" not in self._dev:
+            # (R + r)**2 for disks; r**2 = (0.0 + r)**2 for segments (toi_ball_point, physics.py:120); unused for walls
             disk_r = [float(o.radius) if rec.kind == _lib.BL_OBS_DISK else 0.0
                       for o, rec in zip(self.obstacles, self._obs_records)]
             rs, rs_obs = _lib.pow2_table(self._class_radii, disk_r)
             for q, rec in enumerate(self._obs_records):
-                if rec.kind != _lib.BL_OBS_DISK:
+                if rec.kind == _lib.BL_OBS_WALL:
                     rs_obs[q, :] = 0.0
             self._dev["rsum2"] = torch.from_numpy(rs).to(dev)
             self._dev["rsum2_obs"] = torch.from_numpy(np.ascontiguousarray(rs_obs).reshape(-1)).to(dev) \
@@ -303,6 +304,8 @@ class Billiard:
         obs = self.obstacles[idx]
         if self._obs_records[idx].kind == _lib.BL_OBS_WALL:
             return (obs, (np.float64(arg),))
+        if self._obs_records[idx].kind == _lib.BL_OBS_SEGMENT:
+            return (obs, obs._args(arg))
         return (obs, ())
 
     @property

@@ -201,6 +201,18 @@ int bl_obstacle_resolve(bl_handle *h, const bl_obstacle *obstacle, const double 
     return bl_launch_obstacle_resolve(h, *obstacle, d_in, d_arg, d_out, d_status, m, as_stream(stream));
 }
 
+int bl_toi_ball_point(bl_handle *h, const double *d_in, const double *d_r2, double t_eps, double *d_out, int64_t m,
+                      void *stream) {
+    if (!h) return BL_EINVAL;
+    return bl_launch_point_batch(h, d_in, d_r2, t_eps, d_out, m, as_stream(stream));
+}
+
+int bl_toi_and_param_ball_segment(bl_handle *h, const bl_obstacle *segment, const double *d_in, double t_eps,
+                                  double *d_out_t, double *d_out_u, int32_t *d_out_code, int64_t m, void *stream) {
+    if (!h || !segment) return BL_EINVAL;
+    return bl_launch_segment_param(h, *segment, d_in, t_eps, d_out_t, d_out_u, d_out_code, m, as_stream(stream));
+}
+
 int bl_ensemble_run(bl_handle *h, const bl_obstacle *obstacles_host, int n_obstacles, const double *rsum2_obs_host,
                     double radius, int64_t n_sys, double *d_state, double *d_time, int64_t n_collisions,
                     double end_time, int64_t *d_counts, int32_t *d_hits, int32_t *d_status, void *stream) {

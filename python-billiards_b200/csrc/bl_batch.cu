@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) obstacle_detect_kernel(const bl_obstacle 
     if (q >= m) return;
     const double *r = in + 5 * q;
     double arg;
-    const double rs = (ob.kind == BL_OBS_DISK && rsum2) ? rsum2[q] : 0.0;
+    const double rs = (ob.kind != BL_OBS_WALL && rsum2) ? rsum2[q] : 0.0;
     out_t[q] = bl_obstacle_toi<FMA>(ob, r[0], r[1], r[2], r[3], r[4], rs, arg);
     out_arg[q] = arg;
 }
@@ -52,6 +52,30 @@ __global__ void __launch_bounds__(256) obstacle_resolve_kernel(const bl_obstacle
     double wx = 0, wy = 0;
     status[q] = bl_obstacle_bounce<FMA>(ob, r[0], r[1], r[2], r[3], arg ? arg[q] : 0.0, wx, wy);
     out[2 * q] = wx; out[2 * q + 1] = wy;
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(256) point_batch_kernel(const double *__restrict__ in, const double *__restrict__ r2,
+                                                           const double t_eps, double *__restrict__ out, const long long m) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const double *r = in + 6 * q;
+    out[q] = bl_toi_ball_point<FMA>(r[0], r[1], r[2], r[3], r2[q], r[4], r[5], t_eps);
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(256) segment_param_kernel(const bl_obstacle sg, const double *__restrict__ in,
+                                                             const double t_eps, double *__restrict__ out_t,
+                                                             double *__restrict__ out_u, int32_t *__restrict__ out_code,
+                                                             const long long m) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const double *r = in + 5 * q;
+    double u;
+    int code;
+    out_t[q] = bl_toi_param_ball_segment<FMA>(sg, r[0], r[1], r[2], r[3], r[4], t_eps, u, code);
+    out_u[q] = u;
+    out_code[q] = code;
 }
 
 inline unsigned blocks(long long m) { return (unsigned)((m + 255) / 256); }
@@ -92,4 +116,22 @@ int bl_launch_obstacle_resolve(bl_handle *h, bl_obstacle ob, const double *d_in,
     else obstacle_resolve_kernel<false><<<blocks(m), 256, 0, st>>>(ob, d_in, d_arg, d_out, d_status, m);
     h->launches++;
     return bl_check_cuda(h, cudaGetLastError(), "launch obstacle_resolve_kernel");
+}
+
+int bl_launch_point_batch(bl_handle *h, const double *d_in, const double *d_r2, double t_eps, double *d_out, long long m,
+                          cudaStream_t st) {
+    if (m <= 0) return BL_OK;
+    if (h->dot_fma) point_batch_kernel<true><<<blocks(m), 256, 0, st>>>(d_in, d_r2, t_eps, d_out, m);
+    else point_batch_kernel<false><<<blocks(m), 256, 0, st>>>(d_in, d_r2, t_eps, d_out, m);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch point_batch_kernel");
+}
+
+int bl_launch_segment_param(bl_handle *h, bl_obstacle sg, const double *d_in, double t_eps, double *d_t, double *d_u,
+                            int32_t *d_code, long long m, cudaStream_t st) {
+    if (m <= 0) return BL_OK;
+    if (h->dot_fma) segment_param_kernel<true><<<blocks(m), 256, 0, st>>>(sg, d_in, t_eps, d_t, d_u, d_code, m);
+    else segment_param_kernel<false><<<blocks(m), 256, 0, st>>>(sg, d_in, t_eps, d_t, d_u, d_code, m);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch segment_param_kernel");
 }

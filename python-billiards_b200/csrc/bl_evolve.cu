@@ -111,7 +111,7 @@ struct Layout {
     int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
     int fold;                         // [H][Tb][2] partial candidate of each helper + [H][Tb] ints partner-hit
     int wq;                           // [T/32][4*BL_WQ_CAP] per-warp queue of pairs that reach the sqrt
-    int obs;                          // 5 * n_obs
+    int obs;                          // BL_OBS_WORDS * n_obs
     int misc;                         // 32 words
     int words;
 };
@@ -143,7 +143,7 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.scratch = w; w += 3 * Tb;
     L.fold = w; w += H * Tb * 2 + (H * Tb + 1) / 2;
     L.wq = w; w += ((Tb * H) / 32) * 4 * BL_WQ_CAP;
-    L.obs = w; w += 5 * (n_obs > 0 ? n_obs : 1);
+    L.obs = w; w += BL_OBS_WORDS * (n_obs > 0 ? n_obs : 1);
     L.misc = w; w += 32;
     L.words = w;
     return L;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 
     // ---- load the resident state --------------------------------------------------------------
     const uint64_t ts_inf = bl_sortable(BL_INF);
-    for (int q = tid; q < 5 * n_obs; q += T) sm[L.obs + q] = reinterpret_cast<const uint64_t *>(S.obstacles)[q];
+    for (int q = tid; q < BL_OBS_WORDS * n_obs; q += T) sm[L.obs + q] = reinterpret_cast<const uint64_t *>(S.obstacles)[q];
     const long long seq_base = *S.seq_counter;
     if (primary) {
         if (own) {
@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             const double radius = c_radius[bl];
             for (int q = h; q < n_obs; q += H) {
                 double a;
-                const double rs = obs[q].kind == BL_OBS_DISK ? S.rsum2_obs[(size_t)q * K + myrc] : 0.0;
+                const double rs = obs[q].kind != BL_OBS_WALL ? S.rsum2_obs[(size_t)q * K + myrc] : 0.0;
                 const double t = bl_obstacle_toi<FMA>(obs[q], nx, ny, nvx, nvy, radius, rs, a);
                 if (t < t_min) { t_min = t; q_min = q; arg_min = a; }
             }

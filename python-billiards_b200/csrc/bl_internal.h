@@ -31,6 +31,7 @@ struct bl_handle {
 };
 
 #define BL_MAX_THREADS 1024
+#define BL_OBS_WORDS ((int)(sizeof(bl_obstacle) / 8))
 #define BL_MAX_CTAS 160       // >= SM count
 #define BL_POST_WORDS 16      // header, violation word, BL_R_POST keys of 2 words
 #define BL_R_POST 6           // keys one CTA may post per round
@@ -70,6 +71,10 @@ int bl_launch_obstacle_detect(bl_handle *h, bl_obstacle ob, const double *d_in, 
                               double *d_arg, long long m, cudaStream_t st);
 int bl_launch_obstacle_resolve(bl_handle *h, bl_obstacle ob, const double *d_in, const double *d_arg, double *d_out,
                                int32_t *d_status, long long m, cudaStream_t st);
+int bl_launch_point_batch(bl_handle *h, const double *d_in, const double *d_r2, double t_eps, double *d_out, long long m,
+                          cudaStream_t st);
+int bl_launch_segment_param(bl_handle *h, bl_obstacle sg, const double *d_in, double t_eps, double *d_t, double *d_u,
+                            int32_t *d_code, long long m, cudaStream_t st);
 // bl_ensemble.cu
 int bl_launch_ensemble(bl_handle *h, const bl_obstacle *obs, int n_obs, const double *rsum2_obs, double radius,
                        long long n_sys, double *d_state, double *d_time, long long n_coll, double end_time,

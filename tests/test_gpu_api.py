@@ -109,6 +109,57 @@ def test_infinite_wall(bl):
     assert tuple(c.resolve_collision((0, -10), (10, 1), 1, 1.0)) == (10, -1)
 
 
+def test_line_segment_known_answers(bl):
+    """tests/test_obstacles.py:80-147 and tests/test_physics.py:73-108 of the reference."""
+    from math import cos, pi, sin, sqrt
+    from billiards.physics import toi_and_param_ball_segment, toi_ball_point
+    LineSegment = bl.LineSegment
+    with pytest.raises(ValueError):
+        LineSegment((-1, 0), (-1, 0))
+    line = LineSegment((-1, 0), (1, 0))
+    np.testing.assert_allclose(line._covector, (1 / 2, 0))
+    np.testing.assert_allclose(line._normal, (0, 1))
+    for a in [0, 1 / 6, 1 / 4, -1 / 2, pi / 2 - 1e-6]:      # left end point
+        pos = np.asarray([-cos(a) - 1, sin(a)])
+        vel = np.asarray([cos(a), -sin(a)])
+        assert line.detect_collision(pos, vel, 1 / 2) == (approx(0.5), (0,)), a
+        np.testing.assert_allclose(line.resolve_collision(pos + 0.5 * vel, vel, 1 / 2, 0), (-vel[0], -vel[1]), atol=1e-14)
+    pos, vel = np.asarray([-sqrt(1 / 2) - 2, sqrt(1 / 2) - 1]), np.asarray([1, 1])
+    assert line.detect_collision(pos, vel, 1 + 1e-14) == (approx(1.0), (0,))
+    pos, vel = np.asarray([-2, 1 - 1e-14]), np.asarray([1, 0])
+    assert line.detect_collision(pos, vel, 1) == (approx(1.0), (0,))
+    np.testing.assert_allclose(line.resolve_collision(pos + 1.0 * vel, vel, 1, 0), vel, atol=1e-14)
+    for a in [pi / 2, pi / 2 + 1e-10, pi / 2 + 1e-6, 5 / 6 * pi - 1e-15]:   # along the line
+        pos = np.asarray([-cos(a) - 1, sin(a)])
+        vel = np.asarray([cos(a), -sin(a)])
+        t, (u,) = line.detect_collision(pos, vel, 1 / 2)
+        assert t == approx((pos[1] - 1 / 2) / (-vel[1])), a
+        assert u is not None and u > 0, a
+        np.testing.assert_allclose(line.resolve_collision(pos + t * vel, vel, 1 / 2, u), (vel[0], -vel[1]), atol=1e-14)
+    for a in [0, 1 / 6, 1 / 4, -1 / 2, pi / 2 - 1e-6]:      # right end point
+        pos = np.asarray([-cos(a + pi) + 1, sin(a + pi)])
+        vel = np.asarray([cos(a + pi), -sin(a + pi)])
+        assert line.detect_collision(pos, vel, 1 / 2) == (approx(0.5), (1,)), a
+        np.testing.assert_allclose(line.resolve_collision(pos + 0.5 * vel, vel, 1 / 2, 1), (-vel[0], -vel[1]), atol=1e-14)
+    pos, vel = np.asarray([2, 1 - 1e-14]), np.asarray([-1, 0])
+    assert line.detect_collision(pos, vel, 1) == (approx(1.0), (1,))
+    assert line.detect_collision((0, 5), (0, 1), 0.5) == (INF, (None,))
+    # physics.toi_ball_point
+    assert toi_ball_point((0, 0), (1, 0), 1, (5, 0)) == 4
+    assert toi_ball_point((0, 42), (1, 0), 1, (5, 42)) == 4
+    assert toi_ball_point((2, 0), (1, 0), 1, (0, 0), -0.0) == INF
+    assert toi_ball_point((2, 0), (-1, 0), 1, (0, 0), -0.0) == 1.0
+    assert toi_ball_point((1, 2), (0, -1), sqrt(2), (0, 0), -0.0) == approx(1.0)
+    assert toi_ball_point((1 - 1e-12, 0), (-42, 0), 1, (0, 0), -0.0) == INF
+    # physics.toi_and_param_ball_segment on the segment (0,0)-(1,0)
+    seg = (np.asarray([0, 0]), np.asarray([1.0, 0.0]), np.asarray([0.0, 1.0]))
+    t, u = toi_and_param_ball_segment((0.5, 2), (0, -1), 1, *seg)
+    assert (t, u) == (approx(1.0), approx(0.5))
+    assert toi_and_param_ball_segment((0.5, 2), (0, 1), 1, *seg) == (INF, None)
+    assert toi_and_param_ball_segment((-3, 0.5), (1, 0), 1, *seg) == (INF, 0)
+    assert toi_and_param_ball_segment((4, 0.5), (-1, 0), 1, *seg) == (INF, 1)
+
+
 def test_unsupported_obstacles_fail_loudly(bl):
     class Custom(bl.Obstacle):
         def detect_collision(self, pos, vel, radius):
@@ -116,8 +167,6 @@ def test_unsupported_obstacles_fail_loudly(bl):
 
     with pytest.raises(NotImplementedError):
         bl.Billiard([Custom()])
-    with pytest.raises(NotImplementedError):
-        bl.Billiard([bl.LineSegment((0, 0), (1, 0))])
     with pytest.raises(TypeError):
         bl.Billiard(obstacles=[42])
 

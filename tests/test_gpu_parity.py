@@ -34,6 +34,8 @@ LOGGED = [
     ("dense_gas_1024", lambda: workloads.dense_gas(32), dict(n_events=1000)),
     ("ideal_gas_1024", lambda: workloads.ideal_gas(32), dict(n_events=1000)),
     ("dense_gas_16384", lambda: workloads.dense_gas(128), dict(n_events=100)),
+    ("maze", workloads.maze, dict(n_events=3000)),            # LineSegment obstacles (examples/maze.py)
+    ("maze_wide", workloads.maze_wide, dict(n_events=4000)),  # all four segments, both faces, end points
 ]
 
 
@@ -481,6 +483,79 @@ def test_ensemble_kernel_variants(billiards, oracle):
     assert_bits_equal(ens.balls_velocity, want["v"])
     assert ens.hits.tolist() == want["hits"].tolist()
     assert int(ens.hits.sum()) == 96 * 70000
+
+
+def test_line_segments(billiards, golden, oracle):
+    """f3: LineSegment.  Callback payloads (incl. the line parameter u) of the wide maze against the live reference;
+    3000 random detect / resolve problems; next_ball_obstacle_collision's args; a segment ensemble against the oracle."""
+    g = golden("maze_wide")
+    fma = bool(g["dot_fma"])
+    bld = build(billiards, workloads.maze_wide(), fma)
+    _, (t, i, j, p) = bld.evolve_events(4000, log_capacity=4000, payload=True)
+    assert_bits_equal(t, g["log_t"])
+    assert_bits_equal(p, g["log_payload"], "callback payloads")
+    nb = bld.next_ball_obstacle_collision
+    assert nb[0] == g["end_next_bo"][0] and nb[1] == int(g["end_next_bo"][1])
+    assert bld.obstacles.index(nb[2][0]) == int(g["end_next_bo"][2])
+    s = golden("segment_vectors")
+    from billiards import _lib
+    import torch
+    h = _lib.get_handle(None, fma)
+    dev = h.torch_device
+    n = len(s["rad"])
+    # group the problems by segment and run each group as one batch through the C ABI
+    keys = [tuple(r) for r in s["seg"]]
+    for key in sorted(set(keys)):
+        idx = np.asarray([k for k in range(n) if keys[k] == key and s["vel"][k].any()])
+        rec = _lib.BlObstacle(_lib.BL_OBS_SEGMENT, 0, *key)
+        rows = np.ascontiguousarray(np.concatenate([s["pos"][idx], s["vel"][idx], s["rad"][idx, None]], axis=1))
+        d_in = torch.from_numpy(rows).to(dev)
+        d_r2 = torch.from_numpy(np.asarray([x ** 2 for x in s["rad"][idx].tolist()])).to(dev)
+        d_t = torch.empty(len(idx), dtype=torch.float64, device=dev)
+        d_u = torch.empty(len(idx), dtype=torch.float64, device=dev)
+        d_c = torch.empty(len(idx), dtype=torch.int32, device=dev)
+        h.check(h.lib.bl_obstacle_detect(h.h, rec, _lib.ptr(d_in), _lib.ptr(d_r2), _lib.ptr(d_t), _lib.ptr(d_u),
+                                         len(idx), h.stream()))
+        tt, uu = d_t.cpu().numpy(), d_u.cpu().numpy()
+        assert_bits_equal(tt, s["detect_t"][idx], "LineSegment.detect_collision time")
+        fin = np.isfinite(tt)
+        assert_bits_equal(uu[fin], s["detect_u"][idx][fin], "LineSegment.detect_collision u")
+        h.check(h.lib.bl_toi_and_param_ball_segment(h.h, rec, _lib.ptr(d_in), -1e-10, _lib.ptr(d_t), _lib.ptr(d_u),
+                                                    _lib.ptr(d_c), len(idx), h.stream()))
+        assert_bits_equal(d_t.cpu().numpy(), s["param_t"][idx], "toi_and_param_ball_segment time")
+        assert d_c.cpu().numpy().tolist() == s["param_code"][idx].tolist()
+        face = s["param_code"][idx] == 0
+        assert_bits_equal(d_u.cpu().numpy()[face], s["param_u"][idx][face], "toi_and_param_ball_segment u")
+        # toi_ball_point against the segment's end point
+        rows6 = np.ascontiguousarray(np.concatenate([s["pos"][idx], s["vel"][idx],
+                                                     np.tile(np.asarray(key[6:8]), (len(idx), 1))], axis=1))
+        d_in6 = torch.from_numpy(rows6).to(dev)
+        h.check(h.lib.bl_toi_ball_point(h.h, _lib.ptr(d_in6), _lib.ptr(d_r2), -1e-10, _lib.ptr(d_t), len(idx), h.stream()))
+        assert_bits_equal(d_t.cpu().numpy(), s["point_t"][idx], "toi_ball_point")
+        for u_arg, key_res, col in ((0.37, "resolve_face", 0), (0.0, "resolve_start", 1), (1.0, "resolve_end", 2)):
+            d_arg = torch.full((len(idx),), u_arg, dtype=torch.float64, device=dev)
+            d_w = torch.empty((len(idx), 2), dtype=torch.float64, device=dev)
+            d_st = torch.empty(len(idx), dtype=torch.int32, device=dev)
+            h.check(h.lib.bl_obstacle_resolve(h.h, rec, _lib.ptr(d_in), _lib.ptr(d_arg), _lib.ptr(d_w), _lib.ptr(d_st),
+                                              len(idx), h.stream()))
+            st = d_st.cpu().numpy()
+            assert ((st != 0).astype(int)).tolist() == s["resolve_sep"][idx, col].tolist()
+            ok = st == 0
+            assert_bits_equal(d_w.cpu().numpy()[ok], s[key_res][idx][ok], key_res)
+    # a one-ball-per-system ensemble in the maze against the oracle's loop (generic ensemble kernel)
+    rng = np.random.default_rng(3)
+    cfgm = workloads.maze_wide(num_balls=400, seed=9)
+    pos = np.asarray(cfgm.pos)
+    theta = rng.uniform(0, 2 * np.pi, len(pos))
+    vel = np.stack([np.cos(theta), np.sin(theta)], axis=1)
+    ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, cfgm.obstacles), pos, vel, radius=0.02,
+                                     dot_fma=fma, count_hits=True)
+    ens.run(800)
+    want = oracle.ensemble_run(workloads.oracle_obstacles(cfgm.obstacles), pos, vel, 800, radius=0.02, dot_fma=fma,
+                               count_hits=True)
+    assert_bits_equal(ens.time, want["t"])
+    assert_bits_equal(ens.balls_velocity, want["v"])
+    assert ens.hits.tolist() == want["hits"].tolist()
 
 
 def test_unit_vectors(billiards, golden):

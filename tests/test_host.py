@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     from billiards import _lib
-    assert ctypes.sizeof(_lib.BlObstacle) == 40
+    assert ctypes.sizeof(_lib.BlObstacle) == 72
     assert ctypes.sizeof(_lib.BlSystem) == 16 + 19 * 8
     assert ctypes.sizeof(_lib.BlResult) == 8 * 10 + 8 + 8 * 4 + 128 + 8
     assert ctypes.sizeof(_lib.BlLog) == 40
@@ -83,8 +83,10 @@ def test_host_argument_validation_needs_no_gpu():
         billiards.InfiniteWall((0, 0), (0, 0))
     with pytest.raises(ValueError):
         billiards.InfiniteWall((0, 0), (1, 0), "up")
-    with pytest.raises(NotImplementedError):
-        billiards.Billiard([billiards.LineSegment((0, 0), (1, 1))])
+    with pytest.raises(ValueError):
+        billiards.LineSegment((1, 1), (1, 1))
+    seg = billiards.LineSegment((0, 0), (3, 4))
+    assert seg._covector.tolist() == [3 / 25, 4 / 25] and seg._normal.tolist() == [-4 / 5, 3 / 5]
     b = billiards.Billiard()
     with pytest.raises(ValueError):
         b.add_ball((0, 0, 0))
