@@ -45,6 +45,11 @@ SM_COUNT, FP64_LANES_PER_SM = 148, 64
 # FP64 FMA peak measured on this pool's B200 with tools/microbench.cu (profiles/r1_microbench.log): 37.13 TFLOP/s,
 # 64.0 FMA/clk/SM -- the datasheet formula at the observed clock; used when MEASURED_PEAKS.json has no FP64 entry
 MEASURED_FP64_TFLOPS = 37.13
+# DRAM traffic of the two dominant kernels from their `ncu --set full` captures (profiles/r1_v5_evolve_kernel_ncu_summary.md:
+# dram__bytes_read.sum + dram__bytes_write.sum = 5.829 GB + 5.094 GB for a 20 000-collision launch at N = 16384;
+# profiles/r1_ensemble_ncu_summary.md: 58.8 MB + 6.2 MB for 2^20 systems) -- scaled to the launch timed here
+NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 = (5.829157e9 + 5.094158e9) / 20000
+NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.769408e6 + 6.243840e6) / (1 << 20)
 
 
 def load_peaks():
@@ -178,7 +183,12 @@ def bench_gas(args, device, fma):
     alg_bytes = n_bb * 76.0 * N + n_bo * 68.0 * N
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"kernel": "bl_evolve_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                "traffic": (NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 * (n_bb + n_bo) / max(args.steps, 1)
+                            if N == 16384 else None),
+                "traffic_source": "ncu --set full capture of a 20000-collision launch (profiles/), per collision, "
+                                  "scaled to this launch; row stores 255 KB + 291 KB read per collision",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1),
                 "kernel_ms_per_launch": kernel_ms / max(args.steps, 1),
                 "note": "one launch commits batches of causally independent collisions per grid-wide round; the "
@@ -283,7 +293,9 @@ def bench_ensemble(args, device, fma, rank, world, steps, warmup):
     fp64_peak = MEASURED_FP64_TFLOPS   # TFLOP/s counting fma = 2
     achieved = local_done * FP64_FLOPS_PER_SINAI_COLLISION / (kernel_ms * 1e-3) / 1e12
     roofline = {"kernel": "bl_ensemble_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM * n_local,
+                "traffic_source": "ncu --set full capture (profiles/r1_ensemble_ncu_summary.md): state load + store only",
                 "peak_source": "measured DFMA peak, tools/microbench.cu (profiles/r1_microbench.log); equals "
                                "148 SM x 64 lanes x 2 x 1.96 GHz",
                 "algorithmic_flops_per_collision": FP64_FLOPS_PER_SINAI_COLLISION,
