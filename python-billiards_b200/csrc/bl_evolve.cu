@@ -215,17 +215,24 @@ __device__ __forceinline__ void key_balls(uint64_t code, int &a, int &b) {
     else { a = bl_code_lo(code); b = bl_code_hi(code); }
 }
 
+// collisions per round the parked values have room for: 2 values of 8 bytes per collision and ball
+__host__ __device__ constexpr int pick_m_max(int tb) {
+    return (BL_STASH_BYTES / 16) / tb > BL_M_MAX ? BL_M_MAX : ((BL_STASH_BYTES / 16) / tb < 1 ? 1 : (BL_STASH_BYTES / 16) / tb);
+}
+
 // ---------------------------------------------------------------------------------------------
-template <bool FMA, int MAXT>
+// TB / HH > 0: balls per CTA and threads per ball fixed at compile time (the shape of the large systems), which turns
+// every shared-memory offset into an immediate; 0: taken from the launch parameters
+template <bool FMA, int MAXT, int TB, int HH>
 __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) uint64_t sm[];
     const bl_system &S = P.s;
     const int n = S.n, K = S.n_classes, n_obs = S.n_obstacles;
-    const int Tb = P.Tb, H = P.H, T = Tb * H;
+    const int Tb = TB ? TB : P.Tb, H = HH ? HH : P.H, T = Tb * H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int h = tid / Tb, bl = tid - h * Tb;  // helper h of local ball bl
     const bool primary = h == 0;
-    const int cta = blockIdx.x, ncta = P.ncta, m_max = P.m_max;
+    const int cta = blockIdx.x, ncta = P.ncta, m_max = TB ? pick_m_max(TB) : P.m_max;
     const Layout L = make_layout(Tb, H, m_max, n_obs);
     double *stash = reinterpret_cast<double *>(sm + L.stash);
     double *const bx_b = reinterpret_cast<double *>(sm + L.bx), *const by_b = reinterpret_cast<double *>(sm + L.by);
@@ -1168,16 +1175,9 @@ int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, in
     return rc;
 }
 
-static int pick_m_max(int tb) {
-    int m = (BL_STASH_BYTES / 16) / tb;  // 2 values of 8 bytes per collision and ball
-    if (m > BL_M_MAX) m = BL_M_MAX;
-    if (m < 1) m = 1;
-    return m;
-}
-
-template <bool FMA, int MAXT>
+template <bool FMA, int MAXT, int TB, int HH>
 static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
-    auto kern = bl_evolve_kernel<FMA, MAXT>;
+    auto kern = bl_evolve_kernel<FMA, MAXT, TB, HH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaFuncSetAttribute(smem)");
     const unsigned threads = (unsigned)(P.Tb * P.H);
@@ -1245,7 +1245,10 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     e = cudaMemsetAsync(h->d_bar, 0, 64, st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset barrier");
     h->launches++;
+    if (tb == 128 && hh == 4)
+        return h->dot_fma ? launch_t<true, 512, 128, 4>(h, P, smem, st) : launch_t<false, 512, 128, 4>(h, P, smem, st);
     if (tb * hh <= 512)
-        return h->dot_fma ? launch_t<true, 512>(h, P, smem, st) : launch_t<false, 512>(h, P, smem, st);
-    return h->dot_fma ? launch_t<true, BL_MAX_THREADS>(h, P, smem, st) : launch_t<false, BL_MAX_THREADS>(h, P, smem, st);
+        return h->dot_fma ? launch_t<true, 512, 0, 0>(h, P, smem, st) : launch_t<false, 512, 0, 0>(h, P, smem, st);
+    return h->dot_fma ? launch_t<true, BL_MAX_THREADS, 0, 0>(h, P, smem, st)
+                      : launch_t<false, BL_MAX_THREADS, 0, 0>(h, P, smem, st);
 }
