@@ -100,16 +100,16 @@ struct Layout {
     int w_ts, w_code;                 // [32] warp slots of the exact argmin
     int p0x, p0y, vx, vy, t0;         // [Tb] state of record of my balls
     int mts, mcode, ots;              // [Tb] candidate key, next-obstacle time (sortable)
+    int sts, scode, lts, lcode;       // [Tb] second candidate; key that bounds the rest of the cover from below
     int seq;                          // [Tb] sequence number of the ball's last collision
     int mass, radius, oarg;           // [Tb] doubles
     int oidx, brank, rclass;          // [Tb] ints (brank: [2][Tb])
-    int undo;                         // [11][Tb] state before the optimistic commit of the last batch
+    int undo;                         // [15][Tb] state before the optimistic commit of the last batch
     int bts;                          // [2][m_max] sortable collision times of the batch, by rank
     int obsp;                         // [H][3][Tb] next-obstacle partial minima of the helpers (t, arg, index)
     int hl;                           // ints: [Tb] count, [Tb] partner-hit flag, [Tb][BL_HL_CAP] finite new values of a ball
     int dirty;                        // [Tb] ints
     int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
-    int fold;                         // [H][Tb][2] partial candidate of each helper + [H][Tb] ints partner-hit
     int wq;                           // [T/32][4*BL_WQ_CAP] per-warp queue of pairs that reach the sqrt
     int obs;                          // BL_OBS_WORDS * n_obs
     int misc;                         // 32 words
@@ -132,16 +132,16 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.w_ts = w; w += 32; L.w_code = w; w += 32;
     L.p0x = w; w += Tb; L.p0y = w; w += Tb; L.vx = w; w += Tb; L.vy = w; w += Tb; L.t0 = w; w += Tb;
     L.mts = w; w += Tb; L.mcode = w; w += Tb; L.ots = w; w += Tb;
+    L.sts = w; w += Tb; L.scode = w; w += Tb; L.lts = w; w += Tb; L.lcode = w; w += Tb;
     L.seq = w; w += Tb;
     L.mass = w; w += Tb; L.radius = w; w += Tb; L.oarg = w; w += Tb;
     L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += Tb; L.rclass = w; w += (Tb + 1) / 2;
-    L.undo = w; w += 11 * Tb;
+    L.undo = w; w += 15 * Tb;
     L.bts = w; w += 2 * m_max;
     L.obsp = w; w += 3 * H * Tb;
     L.hl = w; w += (Tb * (BL_HL_CAP + 2) + 1) / 2;
     L.dirty = w; w += (Tb + 1) / 2;
     L.scratch = w; w += 3 * Tb;
-    L.fold = w; w += H * Tb * 2 + (H * Tb + 1) / 2;
     L.wq = w; w += ((Tb * H) / 32) * 4 * BL_WQ_CAP;
     L.obs = w; w += BL_OBS_WORDS * (n_obs > 0 ? n_obs : 1);
     L.misc = w; w += 32;
@@ -249,16 +249,15 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double *st_vx = reinterpret_cast<double *>(sm + L.vx), *st_vy = reinterpret_cast<double *>(sm + L.vy);
     double *st_t0 = reinterpret_cast<double *>(sm + L.t0);
     uint64_t *c_mts = sm + L.mts, *c_mcode = sm + L.mcode, *c_ots = sm + L.ots;
+    uint64_t *c_sts = sm + L.sts, *c_scode = sm + L.scode, *c_lts = sm + L.lts, *c_lcode = sm + L.lcode;
     long long *c_seq = reinterpret_cast<long long *>(sm + L.seq);
     double *c_mass = reinterpret_cast<double *>(sm + L.mass), *c_radius = reinterpret_cast<double *>(sm + L.radius);
     double *c_oarg = reinterpret_cast<double *>(sm + L.oarg);
     int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *const brank_b = reinterpret_cast<int *>(sm + L.brank);
-    uint64_t *const undo = sm + L.undo;  // [f][Tb], f = 0 mts, 1 mcode, 2..6 p0x p0y vx vy t0, 7 ots, 8 oarg, 9 oidx, 10 seq
+    uint64_t *const undo = sm + L.undo;  // [f][Tb], f = 0 mts, 1 mcode, 2..6 p0x p0y vx vy t0, 7 ots, 8 oarg, 9 oidx, 10 seq, 11..14 second candidate and bound
     int *c_rclass = reinterpret_cast<int *>(sm + L.rclass);
     int *dirty = reinterpret_cast<int *>(sm + L.dirty);
     uint64_t *scratch = sm + L.scratch;
-    uint64_t *fold = sm + L.fold;
-    int *fold_hit = reinterpret_cast<int *>(sm + L.fold + H * Tb * 2);
     double *wq = reinterpret_cast<double *>(sm + L.wq);
     const bl_obstacle *obs = reinterpret_cast<const bl_obstacle *>(sm + L.obs);
     int *misc = reinterpret_cast<int *>(sm + L.misc);
@@ -286,12 +285,18 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             c_oarg[bl] = S.obs_arg[k];
             c_oidx[bl] = S.obs_idx[k];
             c_ots[bl] = bl_sortable(S.obs_t[k]);
-            c_mts[bl] = bl_sortable(S.cover_t[k]);
-            c_mcode[bl] = S.cover_code[k];
+            // what the table kernels / the previous launch left: the row minimum (everything else is later), a lower
+            // bound, or nothing
+            const uint64_t ct = bl_sortable(S.cover_t[k]), cc = S.cover_code[k];
+            c_mts[bl] = ct; c_mcode[bl] = cc;
+            c_sts[bl] = ts_inf; c_scode[bl] = BL_CODE_NONE;
+            c_lts[bl] = cc == BL_CODE_NONE ? ts_inf : ct;
+            c_lcode[bl] = cc == BL_CODE_NONE ? BL_CODE_NONE : (cc == BL_CODE_STALE ? 0ull : cc + 1);
         } else {
             st_p0x[bl] = 0; st_p0y[bl] = 0; st_vx[bl] = 0; st_vy[bl] = 0; st_t0[bl] = 0;
             c_seq[bl] = 0; c_rclass[bl] = 0; c_mass[bl] = 0; c_radius[bl] = 0; c_oarg[bl] = 0; c_oidx[bl] = -1;
             c_ots[bl] = ts_inf; c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE;
+            c_sts[bl] = ts_inf; c_scode[bl] = BL_CODE_NONE; c_lts[bl] = ts_inf; c_lcode[bl] = BL_CODE_NONE;
         }
         brank_b[bl] = -1; brank_b[Tb + bl] = -1;
         hl_cnt[bl] = 0; ph[bl] = 0;
@@ -327,18 +332,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     __syncthreads();
     if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 
-    // ---- the two halves of a commit; shared by the optimistic commit, the deferred row stores and the redo ----
-    // helper half: the collisions r = h, h + H, ... < nc_ of a batch (ball list Bbid): store my cells of the
-    // colliding balls' rows and / or fold my new values into one candidate
-    auto helper_pass = [&](const int *Bbid, const int nc_, const int myrank_, const bool mine_, const bool stores,
-                           const bool folds, uint64_t &f_ts, uint64_t &f_code, int &f_hit) {
-        f_ts = ts_inf; f_code = BL_CODE_NONE; f_hit = 0;
+    // ---- pieces of a commit; shared by the optimistic commit, the deferred row stores and the redo ----
+    // row stores of the collisions r = h, h + H, ... < nc_ of a batch (ball list Bbid): my cells of the colliding
+    // balls' rows
+    auto store_pass = [&](const int *Bbid, const int nc_, const int myrank_, const bool mine_) {
         if (!own) return;
-        int q = -1;
-        if (folds) {
-            const uint64_t mcode = c_mcode[bl];
-            if (!mine_ && mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) q = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
-        }
         for (int r = h; r < nc_; r += H) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -347,34 +345,74 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 if (x < 0) continue;
                 if (r == myrank_) {
                     // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
-                    if (stores && x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
+                    if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
                     continue;
                 }
                 if (mine_ && r < myrank_) continue;  // that pair is re-solved at my (later) collision, from x's side
                 // my cell in the row of the ball whose collision is the later one of the pair
-                const double v = stash[(size_t)j * Tb + bl];
-                if (stores) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, v);
-                if (folds) {
-                    if (x == q) f_hit = 1;
-                    if (v < BL_INF) {
-                        const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
-                        if (bl_key_less(vs, vc, f_ts, f_code)) { f_ts = vs; f_code = vc; }
-                    }
-                }
+                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[(size_t)j * Tb + bl]);
             }
         }
     };
-    // primary half: combine the helpers' partial candidates and update the ball
-    auto primary_apply = [&](const double *Bx, const double *By, const double *Bvx, const double *Bvy, const double *Bt,
-                             const int *Bbid, const int myrank_, const bool mine_, uint64_t c_ts, uint64_t c_code,
-                             bool partner_hit, const long long done_base, const bool save_undo, const bool combine) {
-        for (int g = 1; combine && g < H; g++) {
-            const uint64_t t2 = fold[2 * (g * Tb + bl)], c2 = fold[2 * (g * Tb + bl) + 1];
-            if (bl_key_less(t2, c2, c_ts, c_code)) { c_ts = t2; c_code = c2; }
-            partner_hit = partner_hit || fold_hit[g * Tb + bl] != 0;
+    // The cover of my ball after the first nc_ collisions of a batch.  Kept: the two smallest entries E1 < E2 (exact,
+    // current table values) and a key L that bounds every other entry from below; E1 < L makes E1 THE minimum.  An
+    // entry whose partner collided is dropped (its pair has a new value), new finite values below L are inserted,
+    // the third smallest becomes the new L.  No exact entry left: "stale" -- L is all that is known until a repair.
+    //   from_list: the finite new values are listed in hl (optimistic commit) / scan all parked values (redo)
+    auto cover_fold = [&](const int *Bbid, const int nc_, const int myrank_, const bool mine_, const bool from_list,
+                          int dropped /* bit 0: E1's partner collided, bit 1: E2's */) {
+        // the three smallest keys seen, in registers (sentinel = larger than any key)
+        uint64_t k1t = ~0ull, k1c = ~0ull, k2t = ~0ull, k2c = ~0ull, k3t = ~0ull, k3c = ~0ull;
+        auto insert = [&](uint64_t t_, uint64_t c_) {
+            if (!bl_key_less(t_, c_, k3t, k3c)) return;
+            k3t = t_; k3c = c_;
+            if (bl_key_less(k3t, k3c, k2t, k2c)) { const uint64_t tt = k3t, cc = k3c; k3t = k2t; k3c = k2c; k2t = tt; k2c = cc; }
+            if (bl_key_less(k2t, k2c, k1t, k1c)) { const uint64_t tt = k2t, cc = k2c; k2t = k1t; k2c = k1c; k1t = tt; k1c = cc; }
+        };
+        uint64_t lt = c_lts[bl], lc = c_lcode[bl];
+        const uint64_t e1c = c_mcode[bl], e2c = c_scode[bl];
+        int q1 = -1, q2 = -1;
+        if (mine_) {
+            lt = ts_inf; lc = BL_CODE_NONE;  // my cover is emptied: nothing unknown is left
+        } else {
+            const bool has1 = e1c != BL_CODE_STALE && e1c != BL_CODE_NONE, has2 = has1 && e2c != BL_CODE_NONE;
+            if (has1) q1 = bl_code_hi(e1c) == k ? bl_code_lo(e1c) : bl_code_hi(e1c);
+            if (has2) q2 = bl_code_hi(e2c) == k ? bl_code_lo(e2c) : bl_code_hi(e2c);
+            if (!from_list) {
+                dropped = 0;
+                for (int j = 0; j < 2 * nc_; j++) { const int x = Bbid[j]; if (x >= 0) dropped |= (x == q1 ? 1 : 0) | (x == q2 ? 2 : 0); }
+            }
+            if (has1 && !(dropped & 1)) insert(c_mts[bl], e1c);
+            if (has2 && !(dropped & 2)) insert(c_sts[bl], e2c);
         }
-        const uint64_t mts = c_mts[bl], mcode = c_mcode[bl];
-        if (save_undo) { undo[bl] = mts; undo[Tb + bl] = mcode; }
+        const int cnt = from_list ? hl_cnt[bl] : BL_HL_CAP + 1;
+        const int nscan = cnt <= BL_HL_CAP ? cnt : 2 * nc_;
+        for (int i = 0; i < nscan; i++) {
+            const int j = cnt <= BL_HL_CAP ? hl[bl * BL_HL_CAP + i] : i;
+            const int r = j >> 1, x = Bbid[j];
+            if (r >= nc_ || x < 0 || r == myrank_ || (mine_ && r < myrank_)) continue;
+            const double v = stash[(size_t)j * Tb + bl];
+            if (v < BL_INF) {
+                const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
+                if (bl_key_less(vs, vc, lt, lc)) insert(vs, vc);
+            }
+        }
+        if (k3c != ~0ull) { lt = k3t; lc = k3c; }
+        c_lts[bl] = lt; c_lcode[bl] = lc;
+        c_sts[bl] = k2c != ~0ull ? k2t : ts_inf; c_scode[bl] = k2c != ~0ull ? k2c : BL_CODE_NONE;
+        if (k1c != ~0ull) { c_mts[bl] = k1t; c_mcode[bl] = k1c; }
+        else if (lc == BL_CODE_NONE) { c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE; }
+        else { c_mts[bl] = lt; c_mcode[bl] = BL_CODE_STALE; }  // the bound's time is what is posted
+    };
+    // state of record, obstacle entry, sequence number and global mirror of a ball whose collision is committed
+    auto primary_apply = [&](const double *Bx, const double *By, const double *Bvx, const double *Bvy, const double *Bt,
+                             const int *Bbid, const int myrank_, const bool mine_, const long long done_base,
+                             const bool save_undo) {
+        if (save_undo) {
+            undo[bl] = c_mts[bl]; undo[Tb + bl] = c_mcode[bl];
+            undo[11 * Tb + bl] = c_sts[bl]; undo[12 * Tb + bl] = c_scode[bl]; undo[13 * Tb + bl] = c_lts[bl];
+            undo[14 * Tb + bl] = c_lcode[bl];
+        }
         if (mine_) {
             if (save_undo) {
                 undo[2 * Tb + bl] = as_u(st_p0x[bl]); undo[3 * Tb + bl] = as_u(st_p0y[bl]); undo[4 * Tb + bl] = as_u(st_vx[bl]);
@@ -384,8 +422,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             const int myj = Bbid[2 * myrank_] == k ? 2 * myrank_ : 2 * myrank_ + 1;
             const double nx = Bx[myj], ny = By[myj], nvx = Bvx[myj], nvy = Bvy[myj], nt0 = Bt[myj];
-            // my cover is emptied and refilled with the pairs solved at later collisions of the batch
-            c_mts[bl] = c_code != BL_CODE_NONE ? c_ts : ts_inf; c_mcode[bl] = c_code;
             st_p0x[bl] = nx; st_p0y[bl] = ny; st_vx[bl] = nvx; st_vy[bl] = nvy; st_t0[bl] = nt0;
             c_ots[bl] = scratch[3 * bl];
             const double oarg = as_d(scratch[3 * bl + 1]);
@@ -398,14 +434,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             __stcg(S.t0 + k, nt0);
             __stcg(S.obs_arg + k, oarg); __stcg(S.obs_idx + k, oi);
             __stcg(S.seq + k, sq);
-        } else if (mcode == BL_CODE_STALE) {
-            if (c_code != BL_CODE_NONE && c_ts < mts) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }  // strictly earlier: decisive
-        } else if (partner_hit) {
-            // the entry that was my candidate has just been overwritten
-            if (c_code != BL_CODE_NONE && !bl_key_less(mts, mcode, c_ts, c_code)) { c_mts[bl] = c_ts; c_mcode[bl] = c_code; }
-            else c_mcode[bl] = BL_CODE_STALE;  // the old time stays as a lower bound
-        } else if (c_code != BL_CODE_NONE && bl_key_less(c_ts, c_code, mts, mcode)) {
-            c_mts[bl] = c_ts; c_mcode[bl] = c_code;
         }
     };
     // clock, counters and window after nc_ of the nf_ collisions of a batch have been committed
@@ -541,6 +569,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             if (redo) {
                 if (primary && own) {
                     c_mts[bl] = undo[bl]; c_mcode[bl] = undo[Tb + bl];
+                    c_sts[bl] = undo[11 * Tb + bl]; c_scode[bl] = undo[12 * Tb + bl]; c_lts[bl] = undo[13 * Tb + bl];
+                    c_lcode[bl] = undo[14 * Tb + bl];
                     if (prank >= 0 && prank < nf_prev) {
                         const double ox = as_d(undo[2 * Tb + bl]), oy = as_d(undo[3 * Tb + bl]), ovx = as_d(undo[4 * Tb + bl]);
                         const double ovy = as_d(undo[5 * Tb + bl]), ot0 = as_d(undo[6 * Tb + bl]), oarg = as_d(undo[8 * Tb + bl]);
@@ -557,11 +587,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             const int myrank_p = prank >= 0 && prank < nf_prev ? prank : -1;
             const bool mine_p = myrank_p >= 0 && myrank_p < nc;
-            uint64_t f_ts, f_code;
-            int f_hit;
-            if (!redo && myrank_p < 0) {
+            if (myrank_p < 0) {
                 // not a ball of that batch: every parked value is mine to store, four in flight
-                f_ts = ts_inf; f_code = BL_CODE_NONE; f_hit = 0;
                 if (own) {
 #pragma unroll 4
                     for (int j = h; j < 2 * nc; j += H) {
@@ -570,14 +597,14 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     }
                 }
             } else {
-                helper_pass(pbid, nc, myrank_p, mine_p, true, redo, f_ts, f_code, f_hit);
+                store_pass(pbid, nc, myrank_p, mine_p);
             }
             if (redo) {
-                if (H > 1) { fold[2 * (h * Tb + bl)] = f_ts; fold[2 * (h * Tb + bl) + 1] = f_code; fold_hit[h * Tb + bl] = f_hit; }
-                __syncthreads();
-                if (primary && own)
+                if (primary && own) {
+                    cover_fold(pbid, nc, myrank_p, mine_p, false, 0);
                     primary_apply(bx_b + qb * 2 * m_max, by_b + qb * 2 * m_max, bvx_b + qb * 2 * m_max, bvy_b + qb * 2 * m_max,
-                                  pbt, pbid, myrank_p, mine_p, f_ts, f_code, f_hit != 0, u_done, false, true);
+                                  pbt, pbid, myrank_p, mine_p, u_done, false);
+                }
                 advance_clock(pbt, r_info_b + qb * 4 * m_max, nc, nf_prev, u_nE);
                 if (prof_thread) prof[7]++;
             }
@@ -897,8 +924,13 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             if (sel) {
                 const uint64_t ts = scratch[3 * bl];
-                if (ts == ~0ull) { c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE; }
-                else { c_mts[bl] = ts; c_mcode[bl] = bl_pair_code(k, (int)scratch[3 * bl + 1]); }
+                // the exact minimum of everything current in my row: the rest comes later
+                c_sts[bl] = ts_inf; c_scode[bl] = BL_CODE_NONE;
+                if (ts == ~0ull) { c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE; c_lts[bl] = ts_inf; c_lcode[bl] = BL_CODE_NONE; }
+                else {
+                    const uint64_t cc = bl_pair_code(k, (int)scratch[3 * bl + 1]);
+                    c_mts[bl] = ts; c_mcode[bl] = cc; c_lts[bl] = ts; c_lcode[bl] = cc + 1;
+                }
             }
             if (tid == 0) { misc[M_NDIRTY] = 0; if (cta == 0 && ncta > 1) *(P.bar + 4) = 0; }
             if (prof_thread) { prof[3] += clock64() - c0; prof[4]++; n_rescans += nd; }
@@ -972,7 +1004,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         uint64_t vmin = ~0ull;
         const double p0x = st_p0x[bl], p0y = st_p0y[bl], vx = st_vx[bl], vy = st_vy[bl], t0 = st_t0[bl];
         double nx = 0, ny = 0, nvx = 0, nvy = 0, nt0 = 0;   // my state after my own collision (batch balls only)
-        int qpart = -1;  // partner of my current candidate (a ball of the batch overwrites that entry)
+        int qpart = -1, qpart2 = -1;  // partners of my two candidates (a ball of the batch overwrites those entries)
         if (own && myrank >= 0) {
             const int myj = bid[2 * myrank] == k ? 2 * myrank : 2 * myrank + 1;
             nx = bx[myj]; ny = by[myj]; nvx = bvx[myj]; nvy = bvy[myj]; nt0 = bt[myj];
@@ -991,7 +1023,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             obsp[(h * 3 + 2) * Tb + bl] = (uint64_t)(unsigned)q_min;
         } else if (own) {
             const uint64_t mcode = c_mcode[bl];
-            if (mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) qpart = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
+            if (mcode != BL_CODE_STALE && mcode != BL_CODE_NONE) {
+                qpart = bl_code_hi(mcode) == k ? bl_code_lo(mcode) : bl_code_hi(mcode);
+                const uint64_t scode = c_scode[bl];
+                if (scode != BL_CODE_NONE) qpart2 = bl_code_hi(scode) == k ? bl_code_lo(scode) : bl_code_hi(scode);
+            }
         }
         // Pass 1, branch-free: advance my ball to the collision time once, then form the quadratic of
         // physics.py:33-54 against both balls of the collision.  Only ~5 % of the pairs get past the two early
@@ -1014,7 +1050,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     const double st0 = after ? nt0 : t0;
                     const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
                     const int x1 = bid[2 * r + 1];
-                    if (qpart >= 0 && (bid[2 * r] == qpart || x1 == qpart)) ph[bl] = 1;
+                    if (qpart >= 0) {
+                        const int x0 = bid[2 * r];
+                        const int fl = ((x0 == qpart || x1 == qpart) ? 1 : 0) | ((qpart2 >= 0 && (x0 == qpart2 || x1 == qpart2)) ? 2 : 0);
+                        if (fl) atomicOr(&ph[bl], fl);
+                    }
                     {
                         const int j = 2 * r;
                         const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
@@ -1093,23 +1133,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 scratch[3 * bl] = n_ots; scratch[3 * bl + 1] = as_u(arg_min); scratch[3 * bl + 2] = (uint64_t)(unsigned)q_min;
                 if (n_ots <= vbound && myrank < nf - 1) atomicMin(m_viol, (unsigned long long)n_ots);
             }
+            primary_apply(bx, by, bvx, bvy, bt, bid, myrank, mine, done, true);   // saves the undo copy first
             // fold the finite new values of my ball (listed by the solve pass; all of them if the list overflowed)
-            uint64_t c_ts = ts_inf, c_code = BL_CODE_NONE;
-            const int cnt = hl_cnt[bl];
-            const int nscan = cnt <= BL_HL_CAP ? cnt : 2 * nf;
-            for (int i = 0; i < nscan; i++) {
-                const int j = cnt <= BL_HL_CAP ? hl[bl * BL_HL_CAP + i] : i;
-                const int r = j >> 1, x = bid[j];
-                if (x < 0 || r == myrank || (mine && r < myrank)) continue;
-                const double v = stash[(size_t)j * Tb + bl];
-                if (v < BL_INF) {
-                    const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
-                    if (bl_key_less(vs, vc, c_ts, c_code)) { c_ts = vs; c_code = vc; }
-                }
-            }
-            const bool partner_hit = ph[bl] != 0;
+            cover_fold(bid, nf, myrank, mine, true, ph[bl]);
             hl_cnt[bl] = 0; ph[bl] = 0;
-            primary_apply(bx, by, bvx, bvy, bt, bid, myrank, mine, c_ts, c_code, partner_hit, done, true, false);
         }
         u_done = done; u_nbb = n_bb; u_now = now; u_prev_now = prev_now; u_win = win; u_mode = mode; u_kind = kindmask;
         u_nE = nE;
