@@ -635,7 +635,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 __syncthreads();
                 continue;
             }
-            if (primary) pbrank[bl] = -1;
         }
         if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
 
@@ -816,6 +815,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         __syncthreads();
         const int action = misc[M_ACTION];
         int nf = misc[M_NF];
+        if (primary) pbrank[bl] = -1;  // every helper has read its ball's rank in the previous batch by now
         const int nE = misc[M_NE];
         if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
 
