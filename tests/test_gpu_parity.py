@@ -171,6 +171,34 @@ def test_grid_mode_long_run_against_oracle(billiards, oracle, n_side, n_events):
         assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
 
 
+def test_heterogeneous_system_in_grid_mode(billiards, oracle):
+    """~2400 balls with ~250 distinct radii, random masses incl. one infinite and one zero, four walls, a Disk and two
+    LineSegments: radius-class lookups, mass handling and every obstacle kind in the cooperative-grid kernel."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    base = workloads.hetero_gas(side=50, seed=17)
+    segs = [((10.2, 10.3), (20.4, 14.1)), ((35.5, 8.2), (30.1, 22.7))]
+    pos, keep = np.asarray(base.pos), np.ones(base.n, dtype=bool)
+    for a, b in segs:
+        a, b = np.asarray(a), np.asarray(b)
+        u = np.clip(((pos - a) @ (b - a)) / ((b - a) @ (b - a)), 0.0, 1.0)
+        keep &= np.hypot(*(pos - (a + u[:, None] * (b - a))).T) > np.asarray(base.radius) + 0.05
+    cfg = workloads.Config("hetero_grid", base.obstacles + [("segment", a, b) for a, b in segs], pos[keep],
+                           np.asarray(base.vel)[keep], np.asarray(base.radius)[keep], np.asarray(base.mass)[keep])
+    assert cfg.n > 2048
+    n_events = 4000
+    ref, (rt, ri, rj) = _oracle_log(oracle, cfg, fma, n_events)
+    assert (rj <= -6).sum() > 5 and (rj == -5).sum() > 0     # the segments and the disk do get hit
+    bld = build(billiards, cfg, fma)
+    _, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+    assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+    assert_bits_equal(t, rt, "event times")
+    assert_bits_equal(bld.balls_velocity, ref.state()["v"])
+    assert_bits_equal(np.concatenate(bld.toi_table), np.concatenate(ref.toi_table), "toi_table")
+    bt, bi, ot, oo, _ = ref.minima()
+    assert_bits_equal(bld._obstacles_toi, ot)
+
+
 @pytest.mark.parametrize("target", [1, 2, 5, 17, 44])
 def test_batch_size_does_not_change_results(billiards, oracle, target):
     """Collisions per synchronisation round is a speed knob only: same log, same table, same state for every value."""
