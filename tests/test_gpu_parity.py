@@ -290,6 +290,34 @@ def test_batched_rounds_equal_one_at_a_time_over_a_long_run(billiards):
     assert p.min() >= r - 1e-9 and p.max() <= 128.0 - r + 1e-9
 
 
+def test_beyond_16384_balls(billiards, oracle):
+    """32761 balls: more balls than 148 CTAs x 128, so 224 balls per CTA with two helpers each (the run-time shaped
+    kernel variant) and an 8.6 GB table.  First 600 collisions against the oracle, then 30 000 batched vs one per round."""
+    from billiards import _lib
+    import hashlib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.dense_gas(181, seed=4, phi=0.45)
+    ref, (rt, ri, rj) = _oracle_log(oracle, cfg, fma, 600)
+    digests = []
+    for target in (0, 1):
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            _, (t, i, j) = bld.evolve_events(600, log_capacity=600)
+            assert i.tolist() == ri.tolist() and j.tolist() == rj.tolist()
+            assert_bits_equal(t, rt, "event times")
+            _, (t, i, j) = bld.evolve_events(30000, log_capacity=30000)
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        digests.append((hashlib.sha256(t.tobytes() + i.tobytes() + j.tobytes()).hexdigest(),
+                        bld.balls_velocity.copy(), int(bld.last_result.prof[5])))
+        del bld
+    assert digests[0][0] == digests[1][0]
+    assert_bits_equal(digests[0][1], digests[1][1])
+    assert digests[0][2] < 30000 / 8 <= digests[1][2]
+
+
 def test_small_systems_through_the_grid_kernel(billiards, golden):
     """Systems of <= 32 balls normally run in the one-warp kernel; the grid-wide kernel must give the same bits."""
     from billiards import _lib
