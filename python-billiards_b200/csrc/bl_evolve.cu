@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 }
                 if (mine_ && r < myrank_) continue;  // that pair is re-solved at my (later) collision, from x's side
                 // my cell in the row of the ball whose collision is the later one of the pair
-                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[(size_t)j * Tb + bl]);
+                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[j * Tb + bl]);
             }
         }
     };
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             const int j = cnt <= BL_HL_CAP ? hl[bl * BL_HL_CAP + i] : i;
             const int r = j >> 1, x = Bbid[j];
             if (r >= nc_ || x < 0 || r == myrank_ || (mine_ && r < myrank_)) continue;
-            const double v = stash[(size_t)j * Tb + bl];
+            const double v = stash[j * Tb + bl];
             if (v < BL_INF) {
                 const uint64_t vs = bl_sortable(v), vc = bl_pair_code(k, x);
                 if (bl_key_less(vs, vc, lt, lc)) insert(vs, vc);
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 #pragma unroll 4
                     for (int j = h; j < 2 * nc; j += H) {
                         const int x = pbid[j];
-                        if (x >= 0) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[(size_t)j * Tb + bl]);
+                        if (x >= 0) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[j * Tb + bl]);
                     }
                 }
             } else {
@@ -757,8 +757,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t; bts[r] = ts;
                             bid[2 * r] = a; brc[2 * r] = rca;
                             bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
-                            pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
-                            pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
+                            if (want_log) {
+                                pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
+                                pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
+                            }
                             r_info[4 * r] = st; r_info[4 * r + 1] = oi; r_info[4 * r + 2] = 0;
                             if (a >= base && a < base + Tb) brank[a - base] = r;
                         } else {
@@ -778,8 +780,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                             bid[2 * r] = a; brc[2 * r] = rca;
                             bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
                             bid[2 * r + 1] = b; brc[2 * r + 1] = rcb;
-                            pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
-                            pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
+                            if (want_log) {
+                                pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
+                                pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
+                            }
                             r_info[4 * r] = st; r_info[4 * r + 1] = -1; r_info[4 * r + 2] = 1;
                             if (a >= base && a < base + Tb) brank[a - base] = r;
                             if (b >= base && b < base + Tb) brank[b - base] = r;
@@ -1064,7 +1068,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         c0q = bl_sub(bl_dot2<FMA>(dpx, dpy, dpx, dpy), rs);
                         d0 = bl_sub(bl_mul(b0, b0), bl_mul(bl_dot2<FMA>(dvx, dvy, dvx, dvy), c0q));
                         hit0 = valid && !(b0 >= 0.0) && !(d0 <= 0.0);
-                        if (valid) stash[(size_t)j * Tb + bl] = BL_INF;
+                        if (valid) stash[j * Tb + bl] = BL_INF;
                     }
                     if (x1 >= 0) {
                         const int j = 2 * r + 1;
@@ -1075,7 +1079,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         c1q = bl_sub(bl_dot2<FMA>(dpx, dpy, dpx, dpy), rs);
                         d1 = bl_sub(bl_mul(b1, b1), bl_mul(bl_dot2<FMA>(dvx, dvy, dvx, dvy), c1q));
                         hit1 = valid && !(b1 >= 0.0) && !(d1 <= 0.0);
-                        if (valid) stash[(size_t)j * Tb + bl] = BL_INF;
+                        if (valid) stash[j * Tb + bl] = BL_INF;
                     }
                     m0 = __ballot_sync(0xffffffffu, hit0);
                     m1 = __ballot_sync(0xffffffffu, hit1);
@@ -1088,7 +1092,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         const int dst = q_dst[i], j = dst >> 16;
                         const double t1 = bl_div(q_c[i], bl_add(-q_b[i], bl_sqrt(q_d[i])));
                         const double v = bl_add(bt[j], t1 >= BL_T_EPS ? t1 : BL_INF);
-                        stash[(size_t)j * Tb + (dst & 0xffff)] = v;
+                        stash[j * Tb + (dst & 0xffff)] = v;
                         if (v < BL_INF) {  // the few finite values of a ball: all its optimistic fold has to look at
                             const int ob = dst & 0xffff;
                             const int slot = atomicAdd(&hl_cnt[ob], 1);
