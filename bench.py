@@ -237,8 +237,8 @@ def bench_gas(args, device, fma):
                    "ctas_x_threads": list(_evolve_config(h, N)), "dot_fma": bool(fma)},
         "counts": {"ball_ball": n_bb, "ball_obstacle": n_bo, "stale_row_rescans": rescans},
         "phase_cycles_per_round": {k: prof[q] / max(prof[5], 1) for k, q in
-                                   (("post", 8), ("grid_barrier", 9), ("collect", 11), ("validate_and_row_stores", 2),
-                                    ("analyse_resolve", 0), ("solve", 10), ("optimistic_commit", 6), ("repair", 3))},
+                                   (("post", 8), ("grid_barrier", 9), ("collect", 11), ("resolve_and_rank", 2),
+                                    ("batch_cut_beside_row_stores", 0), ("solve", 10), ("optimistic_commit", 6), ("repair", 3))},
         "repair_phases": prof[4], "rounds": prof[5], "reposted_or_redone_rounds": prof[7],
         "collisions_per_round": (n_bb + n_bo) / max(prof[5], 1),
         "build_seconds": build_s,

@@ -63,6 +63,9 @@ enum { KIND_BOTH = 0, KIND_BB = 1, KIND_BO = 2 };
 enum { SYNC_CTA = 0, SYNC_CLUSTER = 1, SYNC_GRID = 2 };
 enum { F_DUP = 1, F_CONFLICT = 2 };
 enum { ACT_BATCH = 0, ACT_OVERFLOW, ACT_EMPTY, ACT_REPAIR, ACT_STOP, ACT_ERROR };
+// a resolved key, by collection slot: QS_D doubles (the log payload: position, old and new velocity of both balls, time;
+// an odd stride keeps the lanes of a warp on different banks) and QS_I ints (status, obstacle, is ball-ball, radius classes)
+enum { QS_D = 13, QS_I = 8 };
 
 struct Params {
     bl_system s;
@@ -110,7 +113,8 @@ struct Layout {
     int hl;                           // ints: [Tb] count, [Tb] partner-hit flag, [Tb][BL_HL_CAP] finite new values of a ball
     int dirty;                        // [Tb] ints
     int scratch;                      // [3*Tb] repair results (ts, partner) / new obstacle entry (ts, arg, idx)
-    int wq;                           // [T/32][4*BL_WQ_CAP] per-warp queue of pairs that reach the sqrt
+    int wq;                           // [T/32][4*BL_WQ_CAP] per-warp queue of pairs that reach the sqrt; between the solves:
+                                      // [BL_SORT_CAP][QS_D] doubles + [BL_SORT_CAP][QS_I] ints, the collected keys resolved
     int obs;                          // BL_OBS_WORDS * n_obs
     int misc;                         // 32 words
     int words;
@@ -142,7 +146,10 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.hl = w; w += (Tb * (BL_HL_CAP + 2) + 1) / 2;
     L.dirty = w; w += (Tb + 1) / 2;
     L.scratch = w; w += 3 * Tb;
-    L.wq = w; w += ((Tb * H) / 32) * 4 * BL_WQ_CAP;
+    {
+        const int q_solve = ((Tb * H) / 32) * 4 * BL_WQ_CAP, q_slots = BL_SORT_CAP * QS_D + BL_SORT_CAP * QS_I / 2;
+        L.wq = w; w += q_solve > q_slots ? q_solve : q_slots;
+    }
     L.obs = w; w += BL_OBS_WORDS * (n_obs > 0 ? n_obs : 1);
     L.misc = w; w += 32;
     L.words = w;
@@ -333,24 +340,46 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     if (P.sync_mode == SYNC_CLUSTER) cluster_sync_all();
 
     // ---- pieces of a commit; shared by the optimistic commit, the deferred row stores and the redo ----
-    // row stores of the collisions r = h, h + H, ... < nc_ of a batch (ball list Bbid): my cells of the colliding
-    // balls' rows
-    auto store_pass = [&](const int *Bbid, const int nc_, const int myrank_, const bool mine_) {
-        if (!own) return;
-        for (int r = h; r < nc_; r += H) {
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int j = 2 * r + u;
-                const int x = Bbid[j];
-                if (x < 0) continue;
-                if (r == myrank_) {
-                    // toi_table[idx2][idx1] = INF, simulation.py:458: my cell in my partner's row
-                    if (x != k) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, BL_INF);
-                    continue;
+    // Row stores of the first nc_ of the nf_ collisions of a batch (ball list Bbid, ranks of my CTA's balls in it Brank):
+    // the parked values of my CTA's columns go to the rows of the colliding balls.  Warp sw of nsw takes one
+    // 32-column tile of one row per step; which thread stores a cell does not matter.
+    auto row_stores = [&](const int *Bbid, const int *Brank, const int nf_, const int nc_, const int sw, const int nsw) {
+        const int segs = Tb >> 5, ntiles = 2 * nc_ * segs;
+        const int dj = nsw / segs, ds = nsw - dj * segs;
+        int j = sw / segs, seg = sw - j * segs;
+        for (int q = sw; q < ntiles; q += nsw) {
+            const int c = (seg << 5) + lane, kc = base + c;
+            const int x = Bbid[j];
+            if (x >= 0 && kc < n) {
+                const int r = j >> 1, pr = Brank[c];
+                const int rk = pr >= 0 && pr < nf_ ? pr : -1;  // rank of ball kc in that batch
+                double *const cell = S.toi + (size_t)x * (size_t)S.pitch + kc;
+                if (r == rk) {
+                    // toi_table[idx2][idx1] = INF, simulation.py:458: the ball's cell in its partner's row
+                    if (x != kc) __stcg(cell, BL_INF);
+                } else if (!(rk >= 0 && rk < nc_ && r < rk)) {
+                    // (skipped: a pair that is re-solved at kc's own, later collision, from x's side)
+                    // the cell in the row of the ball whose collision is the later one of the pair
+                    __stcg(cell, stash[j * Tb + c]);
                 }
-                if (mine_ && r < myrank_) continue;  // that pair is re-solved at my (later) collision, from x's side
-                // my cell in the row of the ball whose collision is the later one of the pair
-                __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[j * Tb + bl]);
+            }
+            j += dj; seg += ds;
+            if (seg >= segs) { seg -= segs; j++; }
+        }
+    };
+    // event log of the first nc_ collisions of a batch, simulation.py:590-594 / :626-631 payloads
+    auto write_log = [&](const double *Br_pay, const int *Br_info, const int *Bbid, const long long first_event,
+                         const int nc_, const int first, const int stride) {
+        for (int r = first; r < nc_; r += stride) {
+            const long long e = first_event + r;
+            const double *pl = Br_pay + 13 * r;
+            const bool bb = Br_info[4 * r + 2] != 0;
+            P.log.t[e] = pl[12]; P.log.i[e] = Bbid[2 * r];
+            P.log.j[e] = bb ? (long long)Bbid[2 * r + 1] : -1 - (long long)Br_info[4 * r + 1];
+            if (P.log.payload) {
+                double *o = P.log.payload + 12 * e;
+#pragma unroll
+                for (int f = 0; f < 12; f++) o[f] = pl[f];
             }
         }
     };
@@ -555,8 +584,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // =========================== 2b. validate the previous batch ===========================================
         // It was committed optimistically (candidates, states, mirrors) before this round's keys were posted; its
         // violation minimum came with the keys.  Normally nothing violates: only the row stores and the log are
-        // left to do.  Otherwise the commit is rolled back and redone for the valid prefix, and the keys -- posted
-        // from a state that never existed -- are thrown away.
+        // left to do, and they run beside warp 0's serial section further down.  Otherwise the commit is rolled back
+        // and redone for the valid prefix, and the keys -- posted from a state that never existed -- are thrown away.
+        int nc_prev = 0;  // collisions of the previous batch whose rows are still to be stored
         if (pending) {
             const uint64_t gmin = (uint64_t)*m_gmin;
             // committed: the first collision always, the others while they come before every violation (the times
@@ -564,9 +594,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             int nc = __popc(__ballot_sync(0xffffffffu, lane < nf_prev && pbts[lane < nf_prev ? lane : 0] < gmin)) +
                      __popc(__ballot_sync(0xffffffffu, lane + 32 < nf_prev && pbts[lane + 32 < nf_prev ? lane + 32 : 0] < gmin));
             if (nc < 1) nc = 1;
-            const bool redo = nc < nf_prev;
-            const int prank = pbrank[bl];
-            if (redo) {
+            pending = false;
+            if (nc < nf_prev) {
+                const int prank = pbrank[bl];
                 if (primary && own) {
                     c_mts[bl] = undo[bl]; c_mcode[bl] = undo[Tb + bl];
                     c_sts[bl] = undo[11 * Tb + bl]; c_scode[bl] = undo[12 * Tb + bl]; c_lts[bl] = undo[13 * Tb + bl];
@@ -584,22 +614,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 }
                 done = u_done; n_bb = u_nbb; now = u_now; prev_now = u_prev_now; win = u_win; mode = u_mode; kindmask = u_kind;
                 __syncthreads();
-            }
-            const int myrank_p = prank >= 0 && prank < nf_prev ? prank : -1;
-            const bool mine_p = myrank_p >= 0 && myrank_p < nc;
-            if (myrank_p < 0) {
-                // not a ball of that batch: every parked value is mine to store, four in flight
-                if (own) {
-#pragma unroll 4
-                    for (int j = h; j < 2 * nc; j += H) {
-                        const int x = pbid[j];
-                        if (x >= 0) __stcg(S.toi + (size_t)x * (size_t)S.pitch + k, stash[j * Tb + bl]);
-                    }
-                }
-            } else {
-                store_pass(pbid, nc, myrank_p, mine_p);
-            }
-            if (redo) {
+                const int myrank_p = prank >= 0 && prank < nf_prev ? prank : -1;
+                const bool mine_p = myrank_p >= 0 && myrank_p < nc;
+                row_stores(pbid, pbrank, nf_prev, nc, warp, nwarps);
+                if (want_log && cta == 0) write_log(r_pay_b + qb * 13 * m_max, r_info_b + qb * 4 * m_max, pbid, u_done, nc, tid, T);
                 if (primary && own) {
                     cover_fold(pbid, nc, myrank_p, mine_p, false, 0);
                     primary_apply(bx_b + qb * 2 * m_max, by_b + qb * 2 * m_max, bvx_b + qb * 2 * m_max, bvy_b + qb * 2 * m_max,
@@ -607,26 +625,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 }
                 advance_clock(pbt, r_info_b + qb * 4 * m_max, nc, nf_prev, u_nE);
                 if (prof_thread) prof[7]++;
-            }
-            // event log, simulation.py:590-594 / :626-631 payloads
-            if (want_log && cta == 0) {
-                const double *const pr_pay = r_pay_b + qb * 13 * m_max;
-                const int *const pr_info = r_info_b + qb * 4 * m_max;
-                for (int r = tid; r < nc; r += T) {
-                    const long long e = u_done + r;
-                    const double *pl = pr_pay + 13 * r;
-                    const bool bb = pr_info[4 * r + 2] != 0;
-                    P.log.t[e] = pl[12]; P.log.i[e] = pbid[2 * r];
-                    P.log.j[e] = bb ? (long long)pbid[2 * r + 1] : -1 - (long long)pr_info[4 * r + 1];
-                    if (P.log.payload) {
-                        double *o = P.log.payload + 12 * e;
-#pragma unroll
-                        for (int f = 0; f < 12; f++) o[f] = pl[f];
-                    }
-                }
-            }
-            pending = false;
-            if (redo) {
                 // start over from the corrected state: drop the collected keys
                 __syncthreads();
                 if (primary) pbrank[bl] = -1;
@@ -635,67 +633,134 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 __syncthreads();
                 continue;
             }
+            nc_prev = nc;
         }
-        if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
 
-        // =========================== 3. analyse + resolve ======================================================
-        // order and conflicts of the collected keys, one (i, j) pair per thread: entry j comes before entry i ->
-        // rank[i]++; and if they share a ball, i is a duplicate (same pair, posted by both balls) or a conflict
-        {
-            const int nr = misc[M_ECOUNT];
-            if (mode == MODE_WINDOW && nr > 1 && nr <= BL_SORT_CAP) {
-                // lane l holds entries l and l + 32; a warp takes entry i, every lane says whether its entries come
-                // before i and whether they share a ball with it: rank and flags of i by ballot
-                const bool h0 = lane < nr, h1 = lane + 32 < nr;
-                const uint64_t t0e = h0 ? e_ts[lane] : ~0ull, c0e = h0 ? e_code[lane] : BL_CODE_END;
-                const uint64_t t1e = h1 ? e_ts[lane + 32] : ~0ull, c1e = h1 ? e_code[lane + 32] : BL_CODE_END;
-                int a0, b0, a1, b1;
-                key_balls(c0e, a0, b0);
-                key_balls(c1e, a1, b1);
-                for (int i = warp; i < nr; i += nwarps) {
-                    const uint64_t ti = e_ts[i], ci = e_code[i];
-                    int a, b;
-                    key_balls(ci, a, b);
-                    const bool p0 = h0 && lane != i && (bl_key_less(t0e, c0e, ti, ci) || (t0e == ti && c0e == ci && lane < i));
-                    const bool p1 = h1 && lane + 32 != i && (bl_key_less(t1e, c1e, ti, ci) || (t1e == ti && c1e == ci && lane + 32 < i));
-                    const bool s0 = p0 && a >= 0 && a0 >= 0, s1 = p1 && a >= 0 && a1 >= 0;
-                    const bool d0 = s0 && a0 == a && b0 == b, d1 = s1 && a1 == a && b1 == b;
-                    const bool x0 = s0 && !d0 && (a0 == a || a0 == b || (b0 >= 0 && (b0 == a || b0 == b)));
-                    const bool x1 = s1 && !d1 && (a1 == a || a1 == b || (b1 >= 0 && (b1 == a || b1 == b)));
-                    const int rk = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
-                    const bool dup = __any_sync(0xffffffffu, d0 || d1), conf = __any_sync(0xffffffffu, x0 || x1);
-                    if (lane == 0) { a_rank[i] = rk; a_flag[i] = (dup ? F_DUP : 0) | (conf ? F_CONFLICT : 0); }
-                }
-                __syncthreads();
-            }
-        }
-        if (warp == 0) {
-            __syncwarp();
-            int nE = misc[M_ECOUNT];
-            int action = misc[M_ACTION] == ACT_OVERFLOW ? ACT_OVERFLOW : ACT_BATCH;
-            int stop_kind = 0, st_status = BL_OK, nf = 0;
-            // sorted entries `lane` and `lane + 32`
-            uint64_t ts0 = ~0ull, cd0 = BL_CODE_END, ts1 = ~0ull, cd1 = BL_CODE_END;
-            int fl0 = 0, fl1 = 0;
-            if (mode == MODE_ARGMIN) {
-                // only the smallest of the per-CTA minima is known to be next
-                for (int i = lane; i < nE && i < BL_EV_CAP; i += 32)
+        // =========================== 3. resolve + rank (all warps) =============================================
+        // Every collected key is resolved speculatively, one thread per key spread over the warps (elastic_collision /
+        // obstacle reflection from the global mirrors), into a record by collection slot; which of them form the batch
+        // is decided afterwards.  While the mirror loads are in flight the warps rank the keys pairwise: entry j comes
+        // before entry i -> rank[i]++; and if they share a ball, i is a duplicate (same pair, posted by both balls) or
+        // a conflict.
+        const int nE_all = misc[M_ECOUNT];
+        double *const qs_d = wq;
+        int *const qs_i = reinterpret_cast<int *>(wq + BL_SORT_CAP * QS_D);
+        if (mode == MODE_ARGMIN) {
+            // only the smallest of the per-CTA minima is known to be next: it moves to slot 0
+            if (warp == 0) {
+                uint64_t ts0 = ~0ull, cd0 = BL_CODE_END;
+                for (int i = lane; i < nE_all && i < BL_EV_CAP; i += 32)
                     if (bl_key_less(e_ts[i], e_code[i], ts0, cd0)) { ts0 = e_ts[i]; cd0 = e_code[i]; }
                 const int w = warp_argmin(ts0, cd0);
                 ts0 = shfl_u64(ts0, w); cd0 = shfl_u64(cd0, w);
-                if (lane != 0) { ts0 = ~0ull; cd0 = BL_CODE_END; }
+                if (lane == 0) { e_ts[0] = ts0; e_code[0] = cd0; }
+            }
+            __syncthreads();
+        }
+        {
+            const int nres = final_stage != 0 ? 0 : (mode == MODE_ARGMIN ? (nE_all > 0 ? 1 : 0) : (nE_all <= BL_SORT_CAP ? nE_all : 0));
+            for (int it = 0, e = lane * nwarps + warp; it == 0 || e < nres; it++, e += T) {
+                uint64_t ts = 0, cd = BL_CODE_END;
+                int a = -1, b = -1;
+                if (e < nres) { ts = e_ts[e]; cd = e_code[e]; key_balls(cd, a, b); }
+                double a0x = 0, a0y = 0, a_vx = 0, a_vy = 0, a_t0 = 0, b0x = 0, b0y = 0, b_vx = 0, b_vy = 0, b_t0 = 0;
+                double m1 = 0 /* obstacle: argument of the hit */, m2 = 0;
+                int rca = 0, rcb = 0 /* obstacle: its index */;
+                if (a >= 0) {
+                    a0x = __ldcg(S.p0x + a); a0y = __ldcg(S.p0y + a); a_vx = __ldcg(S.vx + a); a_vy = __ldcg(S.vy + a);
+                    a_t0 = __ldcg(S.t0 + a);
+                    rca = S.rclass[a];
+                    if (b >= 0) {
+                        b0x = __ldcg(S.p0x + b); b0y = __ldcg(S.p0y + b); b_vx = __ldcg(S.vx + b); b_vy = __ldcg(S.vy + b);
+                        b_t0 = __ldcg(S.t0 + b);
+                        m1 = S.mass[a]; m2 = S.mass[b];
+                        rcb = S.rclass[b];
+                    } else {
+                        m1 = __ldcg(S.obs_arg + a);
+                        rcb = __ldcg(S.obs_idx + a);
+                    }
+                }
+                if (it == 0 && prof_thread) prof[12] += clock64() - c0;
+                if (it == 0 && mode == MODE_WINDOW && nE_all > 1 && nE_all <= BL_SORT_CAP) {
+                    // lane l holds entries l and l + 32; a warp takes entry i, every lane says whether its entries come
+                    // before i and whether they share a ball with it: rank and flags of i by ballot
+                    const int nr = nE_all;
+                    const bool h0 = lane < nr, h1 = lane + 32 < nr;
+                    const uint64_t t0e = h0 ? e_ts[lane] : ~0ull, c0e = h0 ? e_code[lane] : BL_CODE_END;
+                    const uint64_t t1e = h1 ? e_ts[lane + 32] : ~0ull, c1e = h1 ? e_code[lane + 32] : BL_CODE_END;
+                    int a0, b0, a1, b1;
+                    key_balls(c0e, a0, b0);
+                    key_balls(c1e, a1, b1);
+                    for (int i = warp; i < nr; i += nwarps) {
+                        const uint64_t ti = e_ts[i], ci = e_code[i];
+                        int ai, bi;
+                        key_balls(ci, ai, bi);
+                        const bool p0 = h0 && lane != i && (bl_key_less(t0e, c0e, ti, ci) || (t0e == ti && c0e == ci && lane < i));
+                        const bool p1 = h1 && lane + 32 != i && (bl_key_less(t1e, c1e, ti, ci) || (t1e == ti && c1e == ci && lane + 32 < i));
+                        const bool s0 = p0 && ai >= 0 && a0 >= 0, s1 = p1 && ai >= 0 && a1 >= 0;
+                        const bool d0 = s0 && a0 == ai && b0 == bi, d1 = s1 && a1 == ai && b1 == bi;
+                        const bool x0 = s0 && !d0 && (a0 == ai || a0 == bi || (b0 >= 0 && (b0 == ai || b0 == bi)));
+                        const bool x1 = s1 && !d1 && (a1 == ai || a1 == bi || (b1 >= 0 && (b1 == ai || b1 == bi)));
+                        const int rk = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
+                        const bool dup = __any_sync(0xffffffffu, d0 || d1), conf = __any_sync(0xffffffffu, x0 || x1);
+                        if (lane == 0) { a_rank[i] = rk; a_flag[i] = (dup ? F_DUP : 0) | (conf ? F_CONFLICT : 0); }
+                    }
+                }
+                if (it == 0 && prof_thread) prof[13] += clock64() - c0;
+                if (a >= 0) {
+                    const double t = bl_unsortable(ts);
+                    double *const q = qs_d + QS_D * e;
+                    int *const qi = qs_i + QS_I * e;
+                    const double ax = bl_advance(a0x, a_vx, t, a_t0), ay = bl_advance(a0y, a_vy, t, a_t0);
+                    if (b < 0) {
+                        // ball-obstacle, simulation.py:504-519 + :604-636
+                        const int oi = rcb;
+                        double nvx = a_vx, nvy = a_vy;
+                        const int st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, a_vx, a_vy, m1, nvx, nvy) : BL_EASSERT;
+                        q[0] = ax; q[1] = ay; q[2] = a_vx; q[3] = a_vy; q[4] = nvx; q[5] = nvy; q[6] = m1;
+                        q[7] = 0; q[8] = 0; q[9] = 0; q[10] = 0; q[11] = 0; q[12] = t;
+                        qi[0] = st; qi[1] = oi; qi[2] = 0; qi[3] = rca; qi[4] = 0;
+                    } else {
+                        // ball-ball, simulation.py:446-455 + :562-602 (a = idx1 < b = idx2)
+                        const double bxx = bl_advance(b0x, b_vx, t, b_t0), byy = bl_advance(b0y, b_vy, t, b_t0);
+                        bl_remap_masses(m1, m2);
+                        double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
+                        const int st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
+                        q[0] = ax; q[1] = ay; q[2] = a_vx; q[3] = a_vy; q[4] = avx; q[5] = avy;
+                        q[6] = bxx; q[7] = byy; q[8] = b_vx; q[9] = b_vy; q[10] = nbx; q[11] = nby; q[12] = t;
+                        qi[0] = st; qi[1] = -1; qi[2] = 1; qi[3] = rca; qi[4] = rcb;
+                    }
+                }
+            }
+        }
+        if (prof_thread) prof[1] += clock64() - c0;
+        __syncthreads();
+        if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
+
+        // =========================== 3b. the batch (warp 0) beside the previous batch's row stores (the others) ==
+        if (warp == 0) {
+            int nE = nE_all;
+            int action = misc[M_ACTION] == ACT_OVERFLOW ? ACT_OVERFLOW : ACT_BATCH;
+            int stop_kind = 0, st_status = BL_OK, nf = 0;
+            // sorted entries `lane` and `lane + 32`: key, flags, collection slot
+            uint64_t ts0 = ~0ull, cd0 = BL_CODE_END, ts1 = ~0ull, cd1 = BL_CODE_END;
+            int fl0 = 0, fl1 = 0, sl0 = 0, sl1 = 0;
+            if (mode == MODE_ARGMIN) {
                 nE = nE > 0 ? 1 : 0;
+                if (lane == 0 && nE) { ts0 = e_ts[0]; cd0 = e_code[0]; }
             } else if (nE > BL_SORT_CAP) {
                 action = ACT_OVERFLOW;
             } else if (nE == 1) {
                 if (lane == 0) { ts0 = e_ts[0]; cd0 = e_code[0]; }
             } else if (nE > 1) {
                 // into sorted order (ranks and flags come from the pair pass)
-                if (lane < nE) { const int rk = a_rank[lane]; s_ts[rk] = e_ts[lane]; s_code[rk] = e_code[lane]; s_flag[rk] = a_flag[lane]; }
-                if (lane + 32 < nE) { const int rk = a_rank[lane + 32]; s_ts[rk] = e_ts[lane + 32]; s_code[rk] = e_code[lane + 32]; s_flag[rk] = a_flag[lane + 32]; }
+                if (lane < nE) { const int rk = a_rank[lane]; s_ts[rk] = e_ts[lane]; s_code[rk] = e_code[lane]; s_flag[rk] = a_flag[lane] | (lane << 8); }
+                if (lane + 32 < nE) { const int rk = a_rank[lane + 32]; s_ts[rk] = e_ts[lane + 32]; s_code[rk] = e_code[lane + 32]; s_flag[rk] = a_flag[lane + 32] | ((lane + 32) << 8); }
                 __syncwarp();
                 if (lane < nE) { ts0 = s_ts[lane]; cd0 = s_code[lane]; fl0 = s_flag[lane]; }
                 if (lane + 32 < nE) { ts1 = s_ts[lane + 32]; cd1 = s_code[lane + 32]; fl1 = s_flag[lane + 32]; }
+                sl0 = fl0 >> 8; fl0 &= 0xff;
+                sl1 = fl1 >> 8; fl1 &= 0xff;
             }
             const bool max_reached = P.max_events >= 0 && done >= P.max_events;
             if (action == ACT_OVERFLOW) {
@@ -732,7 +797,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     const int r0 = __popc(vm0 & lt_mask), r1 = __popc(vm0) + __popc(vm1 & lt_mask);
                     nf = __popc(vm0) + __popc(vm1);
                     if (nf > allowed) nf = (int)allowed;
-                    // ---- resolve: one lane per collision of the batch (rank r) ----
+                    // ---- the batch tables, by rank r: one lane per collision copies its resolved record ----
                     int er_mine = 0x7fffffff;
                     const int halves = nf > __popc(vm0) ? 2 : 1;
 #pragma unroll 1
@@ -742,52 +807,27 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         if (!((hf ? valid1 : valid0) && r < nf)) continue;
                         int a, b;
                         key_balls(cd, a, b);
-                        int st = BL_OK;
-                        const double t = bl_unsortable(ts);
-                        double *pl = r_pay + 13 * r;
-                        if (cd & BL_CODE_OBS) {
-                            // ball-obstacle, simulation.py:504-519 + :604-636
-                            const double q0x = __ldcg(S.p0x + a), q0y = __ldcg(S.p0y + a), wvx = __ldcg(S.vx + a), wvy = __ldcg(S.vy + a);
-                            const double wt0 = __ldcg(S.t0 + a), qarg = __ldcg(S.obs_arg + a);
-                            const int oi = __ldcg(S.obs_idx + a);
-                            const int rca = S.rclass[a];
-                            const double ax = bl_advance(q0x, wvx, t, wt0), ay = bl_advance(q0y, wvy, t, wt0);
-                            double nvx = wvx, nvy = wvy;
-                            st = oi >= 0 ? bl_obstacle_bounce<FMA>(obs[oi], ax, ay, wvx, wvy, qarg, nvx, nvy) : BL_EASSERT;
-                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = nvx; bvy[2 * r] = nvy; bt[2 * r] = t; bts[r] = ts;
-                            bid[2 * r] = a; brc[2 * r] = rca;
-                            bt[2 * r + 1] = t; bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
-                            if (want_log) {
-                                pl[0] = ax; pl[1] = ay; pl[2] = wvx; pl[3] = wvy; pl[4] = nvx; pl[5] = nvy; pl[6] = qarg;
-                                pl[7] = 0; pl[8] = 0; pl[9] = 0; pl[10] = 0; pl[11] = 0; pl[12] = t;
-                            }
-                            r_info[4 * r] = st; r_info[4 * r + 1] = oi; r_info[4 * r + 2] = 0;
-                            if (a >= base && a < base + Tb) brank[a - base] = r;
+                        const double *const q = qs_d + QS_D * (hf ? sl1 : sl0);
+                        const int *const qi = qs_i + QS_I * (hf ? sl1 : sl0);
+                        const int st = qi[0], bb = qi[2];
+                        const double t = q[12];
+                        bx[2 * r] = q[0]; by[2 * r] = q[1]; bvx[2 * r] = q[4]; bvy[2 * r] = q[5]; bt[2 * r] = t; bts[r] = ts;
+                        bid[2 * r] = a; brc[2 * r] = qi[3];
+                        bt[2 * r + 1] = t;
+                        if (bb) {
+                            bx[2 * r + 1] = q[6]; by[2 * r + 1] = q[7]; bvx[2 * r + 1] = q[10]; bvy[2 * r + 1] = q[11];
+                            bid[2 * r + 1] = b; brc[2 * r + 1] = qi[4];
                         } else {
-                            // ball-ball, simulation.py:446-455 + :562-602 (a = idx1 < b = idx2)
-                            const double a0x = __ldcg(S.p0x + a), a0y = __ldcg(S.p0y + a), a_vx = __ldcg(S.vx + a), a_vy = __ldcg(S.vy + a);
-                            const double a_t0 = __ldcg(S.t0 + a);
-                            const double b0x = __ldcg(S.p0x + b), b0y = __ldcg(S.p0y + b), b_vx = __ldcg(S.vx + b), b_vy = __ldcg(S.vy + b);
-                            const double b_t0 = __ldcg(S.t0 + b);
-                            double m1 = S.mass[a], m2 = S.mass[b];
-                            const int rca = S.rclass[a], rcb = S.rclass[b];
-                            const double ax = bl_advance(a0x, a_vx, t, a_t0), ay = bl_advance(a0y, a_vy, t, a_t0);
-                            const double bxx = bl_advance(b0x, b_vx, t, b_t0), byy = bl_advance(b0y, b_vy, t, b_t0);
-                            bl_remap_masses(m1, m2);
-                            double avx = a_vx, avy = a_vy, nbx = b_vx, nby = b_vy;
-                            st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bxx, byy, b_vx, b_vy, m2, avx, avy, nbx, nby);
-                            bx[2 * r] = ax; by[2 * r] = ay; bvx[2 * r] = avx; bvy[2 * r] = avy; bt[2 * r] = t; bts[r] = ts;
-                            bid[2 * r] = a; brc[2 * r] = rca;
-                            bx[2 * r + 1] = bxx; by[2 * r + 1] = byy; bvx[2 * r + 1] = nbx; bvy[2 * r + 1] = nby; bt[2 * r + 1] = t;
-                            bid[2 * r + 1] = b; brc[2 * r + 1] = rcb;
-                            if (want_log) {
-                                pl[0] = ax; pl[1] = ay; pl[2] = a_vx; pl[3] = a_vy; pl[4] = avx; pl[5] = avy;
-                                pl[6] = bxx; pl[7] = byy; pl[8] = b_vx; pl[9] = b_vy; pl[10] = nbx; pl[11] = nby; pl[12] = t;
-                            }
-                            r_info[4 * r] = st; r_info[4 * r + 1] = -1; r_info[4 * r + 2] = 1;
-                            if (a >= base && a < base + Tb) brank[a - base] = r;
-                            if (b >= base && b < base + Tb) brank[b - base] = r;
+                            bid[2 * r + 1] = -1; brc[2 * r + 1] = 0;
                         }
+                        if (want_log) {
+                            double *pl = r_pay + 13 * r;
+#pragma unroll
+                            for (int f = 0; f < 13; f++) pl[f] = q[f];
+                        }
+                        r_info[4 * r] = st; r_info[4 * r + 1] = qi[1]; r_info[4 * r + 2] = bb;
+                        if (a >= base && a < base + Tb) brank[a - base] = r;
+                        if (b >= base && b < base + Tb) brank[b - base] = r;
                         if (st != BL_OK && r < er_mine) er_mine = r;
                     }
                     if (prof_thread) prof[15] += clock64() - c0;
@@ -816,10 +856,17 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             __syncwarp();
             a_rank[lane] = 0; a_flag[lane] = 0; a_rank[lane + 32] = 0; a_flag[lane + 32] = 0;
         }
+        if (nc_prev > 0 && (warp != 0 || nwarps == 1)) {
+            // the previous batch stands: its rows and log records, by every warp but the one that is busy above
+            const int sw = nwarps == 1 ? 0 : warp - 1, nsw = nwarps == 1 ? 1 : nwarps - 1;
+            row_stores(pbid, pbrank, nf_prev, nc_prev, sw, nsw);
+            if (want_log && cta == 0)
+                write_log(r_pay_b + qb * 13 * m_max, r_info_b + qb * 4 * m_max, pbid, u_done, nc_prev, sw * 32 + lane, nsw * 32);
+        }
         __syncthreads();
         const int action = misc[M_ACTION];
         int nf = misc[M_NF];
-        if (primary) pbrank[bl] = -1;  // every helper has read its ball's rank in the previous batch by now
+        if (primary) pbrank[bl] = -1;  // the row stores have read the ranks of the previous batch by now
         const int nE = misc[M_NE];
         if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
 
@@ -998,7 +1045,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             break;
         }
-        if (prof_thread) { const long long c2 = clock64(); prof[1] += c2 - c0; c0 = c2; }
+        if (prof_thread) c0 = clock64();
 
         // =========================== 4. solve: my ball against the balls of the batch =========================
         // helper h takes the collisions r = h, h + H, ...
