@@ -95,6 +95,7 @@ struct Layout {
     int bx, by, bvx, bvy, bt;         // [2*m_max] batch balls: state right after their collision
     int bid, brc;                     // [2*m_max] ints: ball index (-1: none), radius class
     int e_ts, e_code;                 // [BL_EV_CAP] collected keys (unsorted)
+    int e_ab;                         // [BL_EV_CAP] their balls, two 32-bit words (key_words)
     int s_ts, s_code;                 // [BL_SORT_CAP] sorted keys
     int s_flag, a_rank, a_flag;       // [BL_SORT_CAP] ints: flags in sorted order; rank and flags by collection slot
     int r_pay;                        // [m_max][13] log payload per rank
@@ -127,7 +128,7 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.bx = w; w += 4 * m_max; L.by = w; w += 4 * m_max; L.bvx = w; w += 4 * m_max; L.bvy = w; w += 4 * m_max;
     L.bt = w; w += 4 * m_max;
     L.bid = w; w += 2 * m_max; L.brc = w; w += 2 * m_max;
-    L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP;
+    L.e_ts = w; w += BL_EV_CAP; L.e_code = w; w += BL_EV_CAP; L.e_ab = w; w += BL_EV_CAP;
     L.s_ts = w; w += BL_SORT_CAP; L.s_code = w; w += BL_SORT_CAP;
     L.s_flag = w; w += BL_SORT_CAP / 2; L.a_rank = w; w += BL_SORT_CAP / 2; L.a_flag = w; w += BL_SORT_CAP / 2;
     L.r_pay = w; w += 2 * 13 * m_max;
@@ -222,6 +223,31 @@ __device__ __forceinline__ void key_balls(uint64_t code, int &a, int &b) {
     else { a = bl_code_lo(code); b = bl_code_hi(code); }
 }
 
+// the balls of a key as two 32-bit words for equality tests; absent balls (obstacle hit: the second, stale / none: both)
+// become a word no ball index equals
+#define BL_NO_BALL 0xffffffffu
+__device__ __forceinline__ uint64_t key_words(uint64_t code) {
+    int a, b;
+    key_balls(code, a, b);
+    return (uint64_t)(a >= 0 ? (unsigned)a : BL_NO_BALL) | ((uint64_t)(b >= 0 ? (unsigned)b : BL_NO_BALL) << 32);
+}
+
+// all ones if (tj, cj, j) < (ti, ci, i) lexicographically, else 0: the borrow of a 160-bit subtraction, branch-free
+__device__ __forceinline__ unsigned key_before_mask(uint64_t tj, uint64_t cj, unsigned j, uint64_t ti, uint64_t ci, unsigned i) {
+    unsigned r;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %2;\n\t"
+        "subc.cc.u32 t, %3, %4;\n\t"
+        "subc.cc.u32 t, %5, %6;\n\t"
+        "subc.cc.u32 t, %7, %8;\n\t"
+        "subc.cc.u32 t, %9, %10;\n\t"
+        "subc.u32 %0, 0, 0;\n\t}"
+        : "=r"(r)
+        : "r"(j), "r"(i), "r"((unsigned)cj), "r"((unsigned)ci), "r"((unsigned)(cj >> 32)), "r"((unsigned)(ci >> 32)),
+          "r"((unsigned)tj), "r"((unsigned)ti), "r"((unsigned)(tj >> 32)), "r"((unsigned)(ti >> 32)));
+    return r;
+}
+
 // collisions per round the parked values have room for: 2 values of 8 bytes per collision and ball
 __host__ __device__ constexpr int pick_m_max(int tb) {
     return (BL_STASH_BYTES / 16) / tb > BL_M_MAX ? BL_M_MAX : ((BL_STASH_BYTES / 16) / tb < 1 ? 1 : (BL_STASH_BYTES / 16) / tb);
@@ -247,6 +273,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     double *const bt_b = reinterpret_cast<double *>(sm + L.bt);
     int *const bid_b = reinterpret_cast<int *>(sm + L.bid), *const brc_b = reinterpret_cast<int *>(sm + L.brc);
     uint64_t *e_ts = sm + L.e_ts, *e_code = sm + L.e_code, *s_ts = sm + L.s_ts, *s_code = sm + L.s_code;
+    uint64_t *e_ab = sm + L.e_ab;
     int *s_flag = reinterpret_cast<int *>(sm + L.s_flag), *a_rank = reinterpret_cast<int *>(sm + L.a_rank);
     int *a_flag = reinterpret_cast<int *>(sm + L.a_flag);
     double *const r_pay_b = reinterpret_cast<double *>(sm + L.r_pay);
@@ -319,7 +346,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 
     const bool prof_thread = warp == 0;  // the whole warp reads the clock: a single-lane branch would leave warp 0 diverged
     long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long done = 0, n_bb = 0, n_rescans = 0;
+    long long done = 0, n_bb = 0, n_rescans = 0, prof_rank = 0;
     double now = P.time;   // Billiard.time: time of the last committed collision
     double prev_now = P.time;
     double win = P.window;
@@ -341,30 +368,31 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 
     // ---- pieces of a commit; shared by the optimistic commit, the deferred row stores and the redo ----
     // Row stores of the first nc_ of the nf_ collisions of a batch (ball list Bbid, ranks of my CTA's balls in it Brank):
-    // the parked values of my CTA's columns go to the rows of the colliding balls.  Warp sw of nsw takes one
-    // 32-column tile of one row per step; which thread stores a cell does not matter.
+    // the parked values of my CTA's columns go to the rows of the colliding balls.  Which thread stores a cell does
+    // not matter: warp sw of nsw keeps one 32-column tile and walks down the parked rows with several in flight.
     auto row_stores = [&](const int *Bbid, const int *Brank, const int nf_, const int nc_, const int sw, const int nsw) {
-        const int segs = Tb >> 5, ntiles = 2 * nc_ * segs;
-        const int dj = nsw / segs, ds = nsw - dj * segs;
-        int j = sw / segs, seg = sw - j * segs;
-        for (int q = sw; q < ntiles; q += nsw) {
+        const int segs = Tb >> 5;
+        int seg0, segstep, j0, jstep;
+        if (nsw >= segs) { jstep = nsw / segs; if (sw >= jstep * segs) return; seg0 = sw % segs; segstep = segs; j0 = sw / segs; }
+        else { seg0 = sw; segstep = nsw; j0 = 0; jstep = 1; }
+        for (int seg = seg0; seg < segs; seg += segstep) {
             const int c = (seg << 5) + lane, kc = base + c;
-            const int x = Bbid[j];
-            if (x >= 0 && kc < n) {
-                const int r = j >> 1, pr = Brank[c];
-                const int rk = pr >= 0 && pr < nf_ ? pr : -1;  // rank of ball kc in that batch
-                double *const cell = S.toi + (size_t)x * (size_t)S.pitch + kc;
-                if (r == rk) {
-                    // toi_table[idx2][idx1] = INF, simulation.py:458: the ball's cell in its partner's row
-                    if (x != kc) __stcg(cell, BL_INF);
-                } else if (!(rk >= 0 && rk < nc_ && r < rk)) {
-                    // (skipped: a pair that is re-solved at kc's own, later collision, from x's side)
-                    // the cell in the row of the ball whose collision is the later one of the pair
-                    __stcg(cell, stash[j * Tb + c]);
-                }
+            if (kc >= n) continue;
+            const int pr = Brank[c];
+            const int rk = pr >= 0 && pr < nf_ ? pr : -1;  // rank of ball kc in that batch
+            const int rk_c = rk < nc_ ? rk : -1;           // ... if its collision is committed
+            double *const col = S.toi + kc;
+            const double *const sv = stash + c;
+#pragma unroll 4
+            for (int j = j0; j < 2 * nc_; j += jstep) {
+                const int x = Bbid[j];
+                const int r = j >> 1;
+                // r == rk: toi_table[idx2][idx1] = INF, simulation.py:458, the ball's cell in its partner's row (nothing
+                // on the diagonal); r < rk_c: that pair is re-solved at kc's own, later collision, from x's side;
+                // otherwise the cell in the row of the ball whose collision is the later one of the pair
+                const double v = r == rk ? BL_INF : sv[j * Tb];
+                if (x >= 0 && !(r == rk && x == kc) && !(r < rk_c)) __stcg(col + (size_t)x * (size_t)S.pitch, v);
             }
-            j += dj; seg += ds;
-            if (seg >= segs) { seg -= segs; j++; }
         }
     };
     // event log of the first nc_ collisions of a batch, simulation.py:590-594 / :626-631 payloads
@@ -570,10 +598,13 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 if (vw != ~0ull) atomicMin(m_gmin, (unsigned long long)vw);
                 if (cnt > 0) {
                     const int slot = atomicAdd(&misc[M_ECOUNT], cnt);
-                    if (slot < BL_EV_CAP) { e_ts[slot] = k0.x; e_code[slot] = k0.y; }
-                    if (cnt > 1 && slot + 1 < BL_EV_CAP) { e_ts[slot + 1] = k1.x; e_code[slot + 1] = k1.y; }
+                    if (slot < BL_EV_CAP) { e_ts[slot] = k0.x; e_code[slot] = k0.y; e_ab[slot] = key_words(k0.y); }
+                    if (cnt > 1 && slot + 1 < BL_EV_CAP) { e_ts[slot + 1] = k1.x; e_code[slot + 1] = k1.y; e_ab[slot + 1] = key_words(k1.y); }
                     for (int e = 2; e < cnt; e++)
-                        if (slot + e < BL_EV_CAP) { e_ts[slot + e] = __ldcg(rec + 2 + 2 * e); e_code[slot + e] = __ldcg(rec + 3 + 2 * e); }
+                        if (slot + e < BL_EV_CAP) {
+                            const uint64_t ce = __ldcg(rec + 3 + 2 * e);
+                            e_ts[slot + e] = __ldcg(rec + 2 + 2 * e); e_code[slot + e] = ce; e_ab[slot + e] = key_words(ce);
+                        }
                 }
             }
         }
@@ -643,6 +674,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         // before entry i -> rank[i]++; and if they share a ball, i is a duplicate (same pair, posted by both balls) or
         // a conflict.
         const int nE_all = misc[M_ECOUNT];
+        // Roles of the warps until the batch is known: the first half resolves (waiting on L2 most of the time), the
+        // second half ranks.  (Handing the row stores to a quarter of the warps through both sections was slower.)
+        const int rw = nwarps >= 2 ? nwarps >> 1 : 1;
         double *const qs_d = wq;
         int *const qs_i = reinterpret_cast<int *>(wq + BL_SORT_CAP * QS_D);
         if (mode == MODE_ARGMIN) {
@@ -659,17 +693,18 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         }
         {
             const int nres = final_stage != 0 ? 0 : (mode == MODE_ARGMIN ? (nE_all > 0 ? 1 : 0) : (nE_all <= BL_SORT_CAP ? nE_all : 0));
-            for (int it = 0, e = lane * nwarps + warp; it == 0 || e < nres; it++, e += T) {
-                uint64_t ts = 0, cd = BL_CODE_END;
-                int a = -1, b = -1;
-                if (e < nres) { ts = e_ts[e]; cd = e_code[e]; key_balls(cd, a, b); }
-                double a0x = 0, a0y = 0, a_vx = 0, a_vy = 0, a_t0 = 0, b0x = 0, b0y = 0, b_vx = 0, b_vy = 0, b_t0 = 0;
-                double m1 = 0 /* obstacle: argument of the hit */, m2 = 0;
-                int rca = 0, rcb = 0 /* obstacle: its index */;
-                if (a >= 0) {
-                    a0x = __ldcg(S.p0x + a); a0y = __ldcg(S.p0y + a); a_vx = __ldcg(S.vx + a); a_vy = __ldcg(S.vy + a);
-                    a_t0 = __ldcg(S.t0 + a);
-                    rca = S.rclass[a];
+            if (warp < rw) {
+                for (int e = lane * rw + warp; e < nres; e += 32 * rw) {
+                    const uint64_t ts = e_ts[e], cd = e_code[e];
+                    int a, b;
+                    key_balls(cd, a, b);
+                    if (a < 0) continue;
+                    double b0x = 0, b0y = 0, b_vx = 0, b_vy = 0, b_t0 = 0;
+                    double m1 /* obstacle: argument of the hit */, m2 = 0;
+                    int rcb /* obstacle: its index */;
+                    const double a0x = __ldcg(S.p0x + a), a0y = __ldcg(S.p0y + a), a_vx = __ldcg(S.vx + a), a_vy = __ldcg(S.vy + a);
+                    const double a_t0 = __ldcg(S.t0 + a);
+                    const int rca = S.rclass[a];
                     if (b >= 0) {
                         b0x = __ldcg(S.p0x + b); b0y = __ldcg(S.p0y + b); b_vx = __ldcg(S.vx + b); b_vy = __ldcg(S.vy + b);
                         b_t0 = __ldcg(S.t0 + b);
@@ -679,35 +714,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         m1 = __ldcg(S.obs_arg + a);
                         rcb = __ldcg(S.obs_idx + a);
                     }
-                }
-                if (it == 0 && prof_thread) prof[12] += clock64() - c0;
-                if (it == 0 && mode == MODE_WINDOW && nE_all > 1 && nE_all <= BL_SORT_CAP) {
-                    // lane l holds entries l and l + 32; a warp takes entry i, every lane says whether its entries come
-                    // before i and whether they share a ball with it: rank and flags of i by ballot
-                    const int nr = nE_all;
-                    const bool h0 = lane < nr, h1 = lane + 32 < nr;
-                    const uint64_t t0e = h0 ? e_ts[lane] : ~0ull, c0e = h0 ? e_code[lane] : BL_CODE_END;
-                    const uint64_t t1e = h1 ? e_ts[lane + 32] : ~0ull, c1e = h1 ? e_code[lane + 32] : BL_CODE_END;
-                    int a0, b0, a1, b1;
-                    key_balls(c0e, a0, b0);
-                    key_balls(c1e, a1, b1);
-                    for (int i = warp; i < nr; i += nwarps) {
-                        const uint64_t ti = e_ts[i], ci = e_code[i];
-                        int ai, bi;
-                        key_balls(ci, ai, bi);
-                        const bool p0 = h0 && lane != i && (bl_key_less(t0e, c0e, ti, ci) || (t0e == ti && c0e == ci && lane < i));
-                        const bool p1 = h1 && lane + 32 != i && (bl_key_less(t1e, c1e, ti, ci) || (t1e == ti && c1e == ci && lane + 32 < i));
-                        const bool s0 = p0 && ai >= 0 && a0 >= 0, s1 = p1 && ai >= 0 && a1 >= 0;
-                        const bool d0 = s0 && a0 == ai && b0 == bi, d1 = s1 && a1 == ai && b1 == bi;
-                        const bool x0 = s0 && !d0 && (a0 == ai || a0 == bi || (b0 >= 0 && (b0 == ai || b0 == bi)));
-                        const bool x1 = s1 && !d1 && (a1 == ai || a1 == bi || (b1 >= 0 && (b1 == ai || b1 == bi)));
-                        const int rk = __popc(__ballot_sync(0xffffffffu, p0)) + __popc(__ballot_sync(0xffffffffu, p1));
-                        const bool dup = __any_sync(0xffffffffu, d0 || d1), conf = __any_sync(0xffffffffu, x0 || x1);
-                        if (lane == 0) { a_rank[i] = rk; a_flag[i] = (dup ? F_DUP : 0) | (conf ? F_CONFLICT : 0); }
-                    }
-                }
-                if (it == 0 && prof_thread) prof[13] += clock64() - c0;
-                if (a >= 0) {
                     const double t = bl_unsortable(ts);
                     double *const q = qs_d + QS_D * e;
                     int *const qi = qs_i + QS_I * e;
@@ -731,10 +737,46 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         qi[0] = st; qi[1] = -1; qi[2] = 1; qi[3] = rca; qi[4] = rcb;
                     }
                 }
+                if (prof_thread) prof[13] += clock64() - c0;
             }
+            const long long cr0 = (nwarps >= 2 && warp == rw) ? clock64() : 0;
+            if ((nwarps < 2 || warp >= rw) && mode == MODE_WINDOW && nE_all > 1 && nE_all <= BL_SORT_CAP) {
+                // G neighbouring lanes share entry i; each compares it with every G-th entry j: j comes before i
+                // -> rank[i]++; and if they share a ball, i is a duplicate (same pair) or a conflict
+                const int nr = nE_all;
+                const int pt = nwarps < 2 ? tid : tid - 32 * rw, PT = nwarps < 2 ? T : T - 32 * rw;  // ranking threads
+                const int G = PT >= 256 ? 4 : (PT >= 128 ? 2 : 1);
+                const int c = pt & (G - 1);
+                const unsigned gmask = G == 4 ? 0xfu << (lane & 28) : (G == 2 ? 0x3u << (lane & 30) : 1u << lane);
+                for (int i0 = (pt - lane) / G; i0 < nr; i0 += PT / G) {  // first entry of my warp: one trip count for its lanes
+                    const int i = i0 + lane / G;
+                    const bool act = i < nr;
+                    const uint64_t ti = act ? e_ts[i] : 0, ci = act ? e_code[i] : 0, wi = act ? e_ab[i] : ~0ull;
+                    // my side's absent balls must not equal the other side's
+                    const unsigned Ai = (unsigned)wi == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)wi;
+                    const unsigned Bi = (unsigned)(wi >> 32) == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)(wi >> 32);
+                    int rk = 0, fl = 0;
+#pragma unroll 4
+                    for (int j = c; j < nr; j += G) {
+                        const uint64_t tj = e_ts[j], cj = e_code[j], wj = e_ab[j];
+                        const unsigned before = key_before_mask(tj, cj, (unsigned)j, ti, ci, (unsigned)i);
+                        const unsigned Aj = (unsigned)wj, Bj = (unsigned)(wj >> 32);
+                        const bool share = Aj == Ai || Aj == Bi || Bj == Ai || Bj == Bi;
+                        rk -= (int)before;
+                        fl |= (int)(before & (unsigned)(cj == ci ? F_DUP : (share ? F_CONFLICT : 0)));
+                    }
+                    if (Ai == BL_NO_BALL - 1) fl = 0;  // a key without balls is neither
+                    if (G > 1) {
+                        rk = __reduce_add_sync(gmask, rk);
+                        fl = __reduce_or_sync(gmask, fl);
+                    }
+                    if (act && c == 0) { a_rank[i] = rk; a_flag[i] = fl; }
+                }
+            }
+            if (nwarps >= 2 && warp == rw) prof_rank += clock64() - cr0;
         }
         if (prof_thread) prof[1] += clock64() - c0;
-        __syncthreads();
+        __syncthreads();  // the resolved records and the ranks are in place
         if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
 
         // =========================== 3b. the batch (warp 0) beside the previous batch's row stores (the others) ==
@@ -1208,9 +1250,10 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         S.obs_arg[k] = c_oarg[bl];
     }
     if (tid == 0 && n_rescans) atomicAdd((unsigned long long *)&res->n_rescans, (unsigned long long)n_rescans);
+    if (cta == 0 && lane == 0 && prof_rank) res->prof[12] = prof_rank;  // the first ranking warp's clock
     if (cta == 0 && tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) res->prof[q] = prof[q];
+        for (int q = 0; q < 16; q++) if (q != 12) res->prof[q] = prof[q];
         res->window = win;
         *S.seq_counter = seq_base + done;
     }

@@ -36,7 +36,7 @@ def run(cfg, events, label):
     ms = h.last_kernel_ms()
     prof = [int(x) for x in r.prof]
     rounds = max(prof[5], 1)
-    per = {k: round(prof[q] / rounds) for k, q in (("post", 8), ("barrier1", 9), ("collect", 11), ("..loads issued", 12), ("..ranked", 13), ("..resolved", 1), ("resolve+rank", 2), ("sort", 14), ("..cut+copy", 15), ("..row stores done", 0),
+    per = {k: round(prof[q] / rounds) for k, q in (("post", 8), ("barrier1", 9), ("collect", 11), ("..resolved", 13), ("..rank only", 12), ("resolve+rank", 2), ("sort", 14), ("..cut+copy", 15), ("..row stores done", 0),
                                                     ("solve", 10), ("optimistic commit", 6), ("repair", 3))}
     print(f"{label}: N={cfg.n} events={n} kernel={ms:.2f} ms -> {n / ms * 1e3:,.0f} coll/s ({ms * 1e3 / max(n,1):.2f} us/event); "
           f"rounds {prof[5]} ({n / rounds:.1f} events/round, {prof[7]} re-posted); cycles/round {per}; "
