@@ -118,6 +118,7 @@ struct Layout {
                                       // [BL_SORT_CAP][QS_D] doubles + [BL_SORT_CAP][QS_I] ints, the collected keys resolved
     int obs;                          // BL_OBS_WORDS * n_obs
     int misc;                         // 32 words
+    int prof;                         // 16 words: phase clocks of this CTA (kept out of the registers)
     int words;
 };
 __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_obs) {
@@ -153,6 +154,7 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     }
     L.obs = w; w += BL_OBS_WORDS * (n_obs > 0 ? n_obs : 1);
     L.misc = w; w += 32;
+    L.prof = w; w += 16;
     L.words = w;
     return L;
 }
@@ -345,8 +347,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     const int myrc = c_rclass[bl];
 
     const bool prof_thread = warp == 0;  // the whole warp reads the clock: a single-lane branch would leave warp 0 diverged
-    long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long done = 0, n_bb = 0, n_rescans = 0, prof_rank = 0;
+    // phase clocks: the whole of warp 0 reads the clock, lane 0 adds to the counters in shared memory
+    long long *const prof = reinterpret_cast<long long *>(sm + L.prof);
+    const bool prof_lane = tid == 0;
+    if (tid < 16) prof[tid] = 0;
+    long long done = 0, n_bb = 0, n_rescans = 0;
     double now = P.time;   // Billiard.time: time of the last committed collision
     double prev_now = P.time;
     double win = P.window;
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 
     for (;;) {
         long long c0 = 0;
-        if (prof_thread) { c0 = clock64(); prof[5]++; }
+        if (prof_thread) { c0 = clock64(); if (prof_lane) prof[5]++; }
         // batch tables of this round, and of the previous batch
         double *const bx = bx_b + pb * 2 * m_max, *const by = by_b + pb * 2 * m_max, *const bvx = bvx_b + pb * 2 * m_max;
         double *const bvy = bvy_b + pb * 2 * m_max, *const bt = bt_b + pb * 2 * m_max;
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         if (prof_thread) cb = clock64();
         sync_all(P, epoch);
         if (tid == 0) *m_viol = ~0ull;
-        if (prof_thread) { const long long ce = clock64(); prof[8] += cb - c0; prof[9] += ce - cb; c0 = ce; }
+        if (prof_thread) { const long long ce = clock64(); if (prof_lane) { prof[8] += cb - c0; prof[9] += ce - cb; } c0 = ce; }
         // =========================== 2. collect ==============================================================
         {
             const uint64_t *const box = P.post + (size_t)par * BL_MAX_CTAS * BL_POST_WORDS;
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         }
         par ^= 1;
         __syncthreads();
-        if (prof_thread) { const long long cc = clock64(); prof[11] += cc - c0; c0 = cc; }
+        if (prof_thread) { const long long cc = clock64(); if (prof_lane) prof[11] += cc - c0; c0 = cc; }
 
         // =========================== 2b. validate the previous batch ===========================================
         // It was committed optimistically (candidates, states, mirrors) before this round's keys were posted; its
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                                   pbt, pbid, myrank_p, mine_p, u_done, false);
                 }
                 advance_clock(pbt, r_info_b + qb * 4 * m_max, nc, nf_prev, u_nE);
-                if (prof_thread) prof[7]++;
+                if (prof_lane) prof[7]++;
                 // start over from the corrected state: drop the collected keys
                 __syncthreads();
                 if (primary) pbrank[bl] = -1;
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         qi[0] = st; qi[1] = -1; qi[2] = 1; qi[3] = rca; qi[4] = rcb;
                     }
                 }
-                if (prof_thread) prof[13] += clock64() - c0;
+                if (prof_thread) { const long long cq = clock64(); if (prof_lane) prof[13] += cq - c0; }
             }
             const long long cr0 = (nwarps >= 2 && warp == rw) ? clock64() : 0;
             if ((nwarps < 2 || warp >= rw) && mode == MODE_WINDOW && nE_all > 1 && nE_all <= BL_SORT_CAP) {
@@ -773,11 +778,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     if (act && c == 0) { a_rank[i] = rk; a_flag[i] = fl; }
                 }
             }
-            if (nwarps >= 2 && warp == rw) prof_rank += clock64() - cr0;
+            if (nwarps >= 2 && warp == rw) { const long long cq = clock64(); if (lane == 0) prof[12] += cq - cr0; }  // the first ranking warp's clock
         }
-        if (prof_thread) prof[1] += clock64() - c0;
+        if (prof_thread) { const long long cq = clock64(); if (prof_lane) prof[1] += cq - c0; }
         __syncthreads();  // the resolved records and the ranks are in place
-        if (prof_thread) { const long long cv = clock64(); prof[2] += cv - c0; c0 = cv; }
+        if (prof_thread) { const long long cv = clock64(); if (prof_lane) prof[2] += cv - c0; c0 = cv; }
 
         // =========================== 3b. the batch (warp 0) beside the previous batch's row stores (the others) ==
         if (warp == 0) {
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 else { action = ACT_STOP; stop_kind = max_reached ? BL_STOP_EVENTS : BL_STOP_TIME; }
                 if (lane == 0) { s_ts[0] = ts_inf; s_code[0] = BL_CODE_END; }
             } else {
-                if (prof_thread) prof[14] += clock64() - c0;
+                if (prof_thread) { const long long cq = clock64(); if (prof_lane) prof[14] += cq - c0; }
                 // the batch ends before the first entry that is only a lower bound or shares a ball with an earlier one
                 const unsigned cm0 = __ballot_sync(0xffffffffu, lane < nE && (cd0 == BL_CODE_STALE || (fl0 & F_CONFLICT)));
                 const unsigned cm1 = __ballot_sync(0xffffffffu, lane + 32 < nE && (cd1 == BL_CODE_STALE || (fl1 & F_CONFLICT)));
@@ -872,7 +877,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                         if (b >= base && b < base + Tb) brank[b - base] = r;
                         if (st != BL_OK && r < er_mine) er_mine = r;
                     }
-                    if (prof_thread) prof[15] += clock64() - c0;
+                    if (prof_thread) { const long long cq = clock64(); if (prof_lane) prof[15] += cq - c0; }
                     // a collision that cannot be resolved (physics.py:277-279 / zero masses): commit what comes
                     // before it; if it is the front one, stop with the reference's error
                     const int er = __reduce_min_sync(0xffffffffu, er_mine);
@@ -910,12 +915,12 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         int nf = misc[M_NF];
         if (primary) pbrank[bl] = -1;  // the row stores have read the ranks of the previous batch by now
         const int nE = misc[M_NE];
-        if (prof_thread) { const long long c1 = clock64(); prof[0] += c1 - c0; c0 = c1; }
+        if (prof_thread) { const long long c1 = clock64(); if (prof_lane) prof[0] += c1 - c0; c0 = c1; }
 
         if (action == ACT_OVERFLOW) {  // too many keys below theta: halve the window and post again
             win = bl_mul(win, 0.5);
             if (++shrinks >= 6) mode = MODE_ARGMIN;
-            if (prof_thread) prof[7]++;
+            if (prof_lane) prof[7]++;
             __syncthreads();
             if (tid == 0) misc[M_ACTION] = ACT_BATCH;
             continue;
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         if (action == ACT_EMPTY) {  // empty window: find the true minimum
             mode = MODE_ARGMIN;
             win = bl_mul(win, 2.0);
-            if (prof_thread) prof[7]++;
+            if (prof_lane) prof[7]++;
             continue;
         }
 
@@ -1026,7 +1031,8 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 }
             }
             if (tid == 0) { misc[M_NDIRTY] = 0; if (cta == 0 && ncta > 1) *(P.bar + 4) = 0; }
-            if (prof_thread) { prof[3] += clock64() - c0; prof[4]++; n_rescans += nd; }
+            if (prof_thread) { const long long cq = clock64(); if (prof_lane) { prof[3] += cq - c0; prof[4]++; } }
+            n_rescans += nd;
             __syncthreads();
             continue;
         }
@@ -1200,7 +1206,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 qn += __popc(m1);
             }
         }
-        if (prof_thread) { const long long cs = clock64(); prof[10] += cs - c0; c0 = cs; }
+        if (prof_thread) { const long long cs = clock64(); if (prof_lane) prof[10] += cs - c0; c0 = cs; }
         {
             const uint64_t wmin = warp_min_u64(vmin);
             if (lane == 0 && wmin != ~0ull) atomicMin(m_viol, (unsigned long long)wmin);
@@ -1237,7 +1243,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         pending = true;
         nf_prev = nf;
         pb ^= 1;
-        if (prof_thread) prof[6] += clock64() - c0;
+        if (prof_thread) { const long long cq = clock64(); if (prof_lane) prof[6] += cq - c0; }
         // the barrier of the next post orders this round's mirror stores before anybody reads them
     }
 
@@ -1250,10 +1256,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         S.obs_arg[k] = c_oarg[bl];
     }
     if (tid == 0 && n_rescans) atomicAdd((unsigned long long *)&res->n_rescans, (unsigned long long)n_rescans);
-    if (cta == 0 && lane == 0 && prof_rank) res->prof[12] = prof_rank;  // the first ranking warp's clock
     if (cta == 0 && tid == 0) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) if (q != 12) res->prof[q] = prof[q];
+        for (int q = 0; q < 16; q++) res->prof[q] = prof[q];
         res->window = win;
         *S.seq_counter = seq_base + done;
     }
