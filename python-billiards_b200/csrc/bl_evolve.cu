@@ -82,7 +82,7 @@ struct Params {
     int target;     // collisions per round the window aims at
     int sync_mode;
     double window;  // initial window length (0: unknown)
-    unsigned *bar;  // [0] grid barrier counter, [4] stale-list length (zero at launch)
+    unsigned *bar;  // [0] grid barrier counter, [4] stale-list length, [8] readers' gate (zero at launch)
     uint64_t *post; // [2][BL_MAX_CTAS][BL_POST_WORDS]
     uint64_t *stale_list; // [BL_MAX_CTAS * BL_MAX_THREADS][2] (ball, seq) of the candidates under repair
     uint64_t *partial;    // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     int final_stage = P.query_only ? 1 : 0;  // 0: event loop, 1: report next ball-ball, 2: report next ball-obstacle
     if (final_stage == 1) kindmask = KIND_BB;
     int shrinks = 0;
-    unsigned par = 0, epoch = 0;
+    unsigned par = 0, epoch = 0, reads_epoch = 0;
     const bool want_log = P.log.cap > 0;
     bl_result *const res = P.result;
     // exclusive upper bound of the keys that may be processed: t <= end_time and t < inf
@@ -902,6 +902,16 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             if (lane < BL_R_POST) { pl_ts[lane] = ~0ull; pl_code[lane] = BL_CODE_END; }
             __syncwarp();
             a_rank[lane] = 0; a_flag[lane] = 0; a_rank[lane + 32] = 0; a_flag[lane + 32] = 0;
+        }
+        if (ncta > 1 && tid == T - 1) {
+            // Readers' gate.  The commit further down overwrites the global mirrors of the batch's balls, and a slower
+            // CTA may still be resolving from them: every CTA says here that its mirror loads are done (they were
+            // consumed before the barrier above), and nobody leaves this section -- so nobody commits -- before all
+            // have said so.  A second grid barrier in effect, but it is waited for beside warp 0's serial section
+            // and the row stores instead of on the critical path.
+            reads_epoch += (unsigned)ncta;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar + 8) : "memory");
+            while ((int)(ld_acquire_u32(P.bar + 8) - reads_epoch) < 0) {}
         }
         if (nc_prev > 0 && (warp != 0 || nwarps == 1)) {
             // the previous batch stands: its rows and log records, by every warp but the one that is busy above

@@ -290,6 +290,37 @@ def test_batched_rounds_equal_one_at_a_time_over_a_long_run(billiards):
     assert p.min() >= r - 1e-9 and p.max() <= 128.0 - r + 1e-9
 
 
+def test_short_rounds_do_not_race_with_slower_ctas(billiards):
+    """One collision per round makes the rounds so short that a CTA reaches its commit (which overwrites the global
+    mirrors of the colliding balls) while a slower CTA may still be resolving from them -- unless the readers' gate
+    holds it back.  Repeated runs of that schedule, with launches of another shape in between, must all give the
+    log of the batched schedule."""
+    from billiards import _lib
+    import hashlib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg, other = workloads.dense_gas(128), workloads.dense_gas(47, seed=11)
+    n_events = 40000
+
+    def run(target):
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            counts, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        return counts, hashlib.sha256(t.tobytes() + i.tobytes() + j.tobytes()).hexdigest(), bld.balls_velocity.copy()
+
+    want = run(0)
+    for rep in range(8):
+        o = build(billiards, other, fma)
+        for k in (1, 2, 3, 5, 64, 257, 11):
+            o.evolve_events(k, log_capacity=k)
+        got = run(1)
+        assert got[0] == want[0] and got[1] == want[1], f"repetition {rep}: one collision per round differs"
+        assert_bits_equal(got[2], want[2], "velocities")
+
+
 def test_beyond_16384_balls(billiards, oracle):
     """32761 balls: more balls than 148 CTAs x 128, so 224 balls per CTA with two helpers each (the run-time shaped
     kernel variant) and an 8.6 GB table.  First 600 collisions against the oracle, then 30 000 batched vs one per round."""
