@@ -1359,11 +1359,14 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.result = h->d_result;
     P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
     P.m_max = pick_m_max(tb);
-    // collisions per round the window aims at: the chance that a round is cut short by a violation grows like
-    // m^2 / n, the synchronisation cost per collision falls like 1 / m (measured optimum ~ sqrt(n / 8))
+    // Keys per round the window aims at (about half of them become collisions of the batch: the rest are the same pair
+    // posted twice, or lie behind the first conflict).  The chance that a round is cut short grows like m^2 / n, the
+    // synchronisation cost per collision falls like 1 / m; measured optimum on B200 ~ sqrt(n / 2) (N = 256: 12,
+    // 1024: 24, 2025: 32, 4096: 40-48, >= 8100: 52-60 -- profiles/r1_target_scan.log).
     int target = 1;
-    while ((long long)(target + 1) * (target + 1) * 8 <= (long long)s->n) target++;
-    if (target > P.m_max + 2) target = P.m_max + 2;  // keys, of which about a third are the same pair posted twice
+    while ((long long)(target + 1) * (target + 1) * 2 <= (long long)s->n) target++;
+    if (target > BL_SORT_CAP - 8) target = BL_SORT_CAP - 8;
+    if (target > 2 * P.m_max) target = 2 * P.m_max;
     if (target < 1) target = 1;
     if (h->target_override > 0) target = h->target_override < BL_SORT_CAP - 4 ? h->target_override : BL_SORT_CAP - 4;
     P.target = target;
