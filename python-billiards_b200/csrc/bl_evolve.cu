@@ -699,7 +699,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
         {
             const int nres = final_stage != 0 ? 0 : (mode == MODE_ARGMIN ? (nE_all > 0 ? 1 : 0) : (nE_all <= BL_SORT_CAP ? nE_all : 0));
             if (warp < rw) {
-                for (int e = lane * rw + warp; e < nres; e += 32 * rw) {
+                // (consecutive lanes write consecutive records: the odd record stride keeps them on different banks)
+                const int per = (BL_SORT_CAP + rw - 1) / rw;
+                for (int e = warp * per + lane; e < nres && e < (warp + 1) * per; e += 32) {
                     const uint64_t ts = e_ts[e], cd = e_code[e];
                     int a, b;
                     key_balls(cd, a, b);
