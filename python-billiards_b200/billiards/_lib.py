@@ -62,6 +62,7 @@ SIGNATURES = {
     "bl_last_error": (ctypes.c_char_p, [_H]),
     "bl_version": (ctypes.c_char_p, []),
     "bl_recompute": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, ctypes.c_int, c_void]),
+    "bl_recompute_range": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.c_int, ctypes.c_int, c_void]),
     "bl_apply_edits": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void, c_void]),
     "bl_host_pow2_table": (ctypes.c_int, [c_double_p, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, c_double_p]),
     "bl_rebuild_cover": (ctypes.c_int, [_H, _SYS, c_void]),

@@ -58,7 +58,8 @@ class Billiard:
         self._cap = 0          # capacity of the per-ball device buffers
         self._pitch = 0        # row pitch of the table
         self._dev = {}         # name -> torch tensor
-        self._pending = []     # (pos, vel, radius, mass, add_time) not yet on the device
+        self._pending = []     # chunks (pos[k,2], vel[k,2], add_time) not yet on the device
+        self._n_pending = 0
 
         # host mirrors (valid when _host_valid)
         self._pos = np.empty((0, 2), dtype=np.float64)
@@ -147,10 +148,19 @@ class Billiard:
         import torch
         h = self._h()
         grew = False
-        for r in self.balls_radius[first:last]:
-            if r not in self._classes:
-                self._classes[r] = len(self._class_radii)
-                self._class_radii.append(r)
+        radii = self.balls_radius[first:last]
+        r = np.asarray(radii, dtype=np.float64)
+        inv = None
+        if len(radii) > 256 and np.isfinite(r).all():
+            # many balls, few radii: classify the distinct values only
+            distinct, inv = np.unique(r, return_inverse=True)
+            distinct = distinct.tolist()
+        else:
+            distinct = radii
+        for x in distinct:
+            if x not in self._classes:
+                self._classes[x] = len(self._class_radii)
+                self._class_radii.append(x)
                 grew = True
         dev = h.torch_device
         if grew or "rsum2" not in self._dev:
@@ -164,8 +174,10 @@ class Billiard:
             self._dev["rsum2"] = torch.from_numpy(rs).to(dev)
             self._dev["rsum2_obs"] = torch.from_numpy(np.ascontiguousarray(rs_obs).reshape(-1)).to(dev) \
                 if rs_obs.size else torch.zeros(1, dtype=torch.float64, device=dev)
-        r = np.asarray(self.balls_radius[first:last], dtype=np.float64)
-        c = np.asarray([self._classes[x] for x in self.balls_radius[first:last]], dtype=np.int32)
+        if inv is not None:
+            c = np.asarray([self._classes[x] for x in distinct], dtype=np.int32)[inv]
+        else:
+            c = np.asarray([self._classes[x] for x in radii], dtype=np.int32)
         self._dev["radius"][first:last] = torch.from_numpy(r).to(dev)
         self._dev["rclass"][first:last] = torch.from_numpy(c).to(dev)
         self._radius_up[first:last] = self.balls_radius[first:last]
@@ -183,27 +195,26 @@ class Billiard:
             return
         h = self._h()
         self._table_sync()
-        first, k = self._n, len(self._pending)
+        first, k = self._n, self._n_pending
         last = first + k
         self._alloc(last)
         dev = h.torch_device
-        pos = np.asarray([p[0] for p in self._pending], dtype=np.float64).reshape(k, 2)
-        vel = np.asarray([p[1] for p in self._pending], dtype=np.float64).reshape(k, 2)
-        t_add = np.asarray([p[4] for p in self._pending], dtype=np.float64)
+        pos = np.concatenate([c[0] for c in self._pending], axis=0).reshape(k, 2)
+        vel = np.concatenate([c[1] for c in self._pending], axis=0).reshape(k, 2)
+        t_add = np.concatenate([np.full(c[0].shape[0], c[2], dtype=np.float64) for c in self._pending])
         d = self._dev
-        d["p0x"][first:last] = torch.from_numpy(np.ascontiguousarray(pos[:, 0])).to(dev)
-        d["p0y"][first:last] = torch.from_numpy(np.ascontiguousarray(pos[:, 1])).to(dev)
-        d["vx"][first:last] = torch.from_numpy(np.ascontiguousarray(vel[:, 0])).to(dev)
-        d["vy"][first:last] = torch.from_numpy(np.ascontiguousarray(vel[:, 1])).to(dev)
-        d["t0"][first:last] = torch.from_numpy(t_add).to(dev)
+        # one host -> device copy for the five state arrays
+        packed = torch.from_numpy(np.ascontiguousarray(np.stack([pos[:, 0], pos[:, 1], vel[:, 0], vel[:, 1], t_add]))).to(dev)
+        for q, name in enumerate(("p0x", "p0y", "vx", "vy", "t0")):
+            d[name][first:last] = packed[q]
         self._n = last
         self._radius_up.extend([None] * k)
         self._upload_radii(first, last)
         self._upload_masses()
         self._pending = []
-        idx = torch.arange(first, last, dtype=torch.int32, device=dev)
+        self._n_pending = 0
         s = self._system()
-        h.check(h.lib.bl_recompute(h.h, ctypes.byref(s), float(self._time), _lib.ptr(idx), k, h.stream()))
+        h.check(h.lib.bl_recompute_range(h.h, ctypes.byref(s), float(self._time), first, k, h.stream()))
         h.check(h.lib.bl_rebuild_cover(h.h, ctypes.byref(s), h.stream()))
         self._next = None
 
@@ -248,7 +259,7 @@ class Billiard:
     @property
     def count(self):
         """Number of balls in the billiard."""
-        return self._n + len(self._pending)
+        return self._n + self._n_pending
 
     def _get(self, name):
         self._sync_host()
@@ -373,7 +384,8 @@ class Billiard:
         radius, mass = float(radius), float(mass)  # TypeError for None, like the reference
         self._sync_host()
         idx = self.count
-        self._pending.append((p, v, radius, mass, self._time))
+        self._pending.append((p.reshape(1, 2).copy(), v.reshape(1, 2).copy(), self._time))
+        self._n_pending += 1
         self.balls_radius.append(radius)
         self.balls_mass.append(mass)
         self._pos = np.append(self._pos, [p], axis=0)
@@ -551,7 +563,9 @@ class Billiard:
         self._sync_host()
         first = self.count
         t = self._time
-        self._pending.extend((pos[q], vel[q], radius[q], mass[q], t) for q in range(k))
+        if k:
+            self._pending.append((pos.copy(), vel.copy(), t))
+            self._n_pending += k
         self.balls_radius.extend(radius)
         self.balls_mass.extend(mass)
         self._pos = np.concatenate([self._pos, pos], axis=0)

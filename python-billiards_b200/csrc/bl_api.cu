@@ -92,7 +92,16 @@ static int check_system(bl_handle *h, const bl_system *s) {
 int bl_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, void *stream) {
     int rc = check_system(h, s);
     if (rc) return rc;
-    return bl_launch_recompute(h, s, time, d_idx, k, as_stream(stream));
+    if (!d_idx && k > 0) return bl_set_error(h, BL_EINVAL, "bl_recompute: no index list");
+    return bl_launch_recompute(h, s, time, d_idx, 0, k, as_stream(stream));
+}
+
+int bl_recompute_range(bl_handle *h, const bl_system *s, double time, int first, int k, void *stream) {
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    if (k > 0 && (first < 0 || first + k > s->n))
+        return bl_set_error(h, BL_EINVAL, "bl_recompute_range: balls %d..%d of %d", first, first + k - 1, s->n);
+    return bl_launch_recompute(h, s, time, nullptr, first, k, as_stream(stream));
 }
 
 int bl_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,

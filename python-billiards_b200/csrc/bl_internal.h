@@ -55,7 +55,8 @@ int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double
                            int first_kind, const bl_log *log, int query_only, cudaStream_t st);
 int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode);
 // bl_table.cu
-int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st);
+int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int first, int k,
+                        cudaStream_t st);  // d_idx == nullptr: balls first .. first + k - 1
 int bl_launch_rebuild_cover(bl_handle *h, const bl_system *s, cudaStream_t st);
 int bl_launch_symmetrize(bl_handle *h, const bl_system *s, cudaStream_t st);
 int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_t *d_idx, cudaStream_t st);

@@ -14,10 +14,14 @@
 
 namespace {
 
+// idx == nullptr: the listed balls are range_first, range_first + 1, ... -- a pair of two listed balls is then solved by
+// both of them (the solve is bit-symmetric in the two balls), so each stores only the cell of its own row: no
+// strided stores into the other triangle when a whole table is built
 template <bool FMA>
 __global__ void __launch_bounds__(256) bl_recompute_kernel(const bl_system S, const double time,
-                                                            const int32_t *__restrict__ idx) {
-    const int i = idx[blockIdx.y];
+                                                            const int32_t *__restrict__ idx, const int range_first,
+                                                            const int range_count) {
+    const int i = idx ? idx[blockIdx.y] : range_first + (int)blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= S.n) return;
     const size_t pitch = (size_t)S.pitch;
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(256) bl_recompute_kernel(const bl_system S, co
     // _detect_ball_collision: time + toi_ball_ball (bit-symmetric in the two balls)
     const double v = bl_add(time, bl_toi_ball_ball<FMA>(ipx, ipy, ivx, ivy, jpx, jpy, jvx, jvy, rs));
     S.toi[(size_t)i * pitch + j] = v;
-    S.toi[(size_t)j * pitch + i] = v;
+    if (idx || j < range_first || j >= range_first + range_count) S.toi[(size_t)j * pitch + i] = v;
 }
 
 __device__ __forceinline__ void warp_min_key(uint64_t &ts, uint64_t &cd) {
@@ -159,14 +163,17 @@ int bl_launch_apply_edits(bl_handle *h, const bl_system *s, double time, const d
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_apply_edits_kernel");
 }
 
-int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, cudaStream_t st) {
+int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int first, int k,
+                        cudaStream_t st) {
     if (k <= 0 || s->n <= 0) return BL_OK;
     const int chunk = 32768;  // gridDim.y limit is 65535
     for (int off = 0; off < k; off += chunk) {
         const int kk = k - off < chunk ? k - off : chunk;
         dim3 grid((unsigned)((s->n + 255) / 256), (unsigned)kk, 1);
-        if (h->dot_fma) bl_recompute_kernel<true><<<grid, 256, 0, st>>>(*s, time, d_idx + off);
-        else bl_recompute_kernel<false><<<grid, 256, 0, st>>>(*s, time, d_idx + off);
+        // (a chunk of a range still skips the mirror stores for the whole range: every ball of it is solved)
+        const int32_t *ix = d_idx ? d_idx + off : nullptr;
+        if (h->dot_fma) bl_recompute_kernel<true><<<grid, 256, 0, st>>>(*s, time, ix, first + off, k - off);
+        else bl_recompute_kernel<false><<<grid, 256, 0, st>>>(*s, time, ix, first + off, k - off);
         h->launches++;
     }
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_recompute_kernel");
