@@ -98,13 +98,11 @@ class BilliardEnsemble:
 
     @property
     def balls_initial_position(self):
-        s = self._state.cpu().numpy()
-        return np.ascontiguousarray(s[0:2].T)
+        return self._state[0:2].T.contiguous().cpu().numpy()  # transposed on the device, one copy of what is asked for
 
     @property
     def balls_velocity(self):
-        s = self._state.cpu().numpy()
-        return np.ascontiguousarray(s[2:4].T)
+        return self._state[2:4].T.contiguous().cpu().numpy()
 
     def positions_at(self, time):
         """ball positions at a common ``time`` (p0 + v*(time - t0), valid until each system's next collision)"""
