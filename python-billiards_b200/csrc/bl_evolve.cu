@@ -52,6 +52,7 @@
 // are made exact again only when they come near the front of the queue.  The global minimum over {m[k]} equals
 // the minimum over the whole table.
 #include <cstdio>
+#include <type_traits>
 
 #include "bl_arith.cuh"
 #include "bl_internal.h"
@@ -752,33 +753,42 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 // -> rank[i]++; and if they share a ball, i is a duplicate (same pair) or a conflict
                 const int nr = nE_all;
                 const int pt = nwarps < 2 ? tid : tid - 32 * rw, PT = nwarps < 2 ? T : T - 32 * rw;  // ranking threads
-                const int G = PT >= 256 ? 4 : (PT >= 128 ? 2 : 1);
-                const int c = pt & (G - 1);
-                const unsigned gmask = G == 4 ? 0xfu << (lane & 28) : (G == 2 ? 0x3u << (lane & 30) : 1u << lane);
-                for (int i0 = (pt - lane) / G; i0 < nr; i0 += PT / G) {  // first entry of my warp: one trip count for its lanes
-                    const int i = i0 + lane / G;
-                    const bool act = i < nr;
-                    const uint64_t ti = act ? e_ts[i] : 0, ci = act ? e_code[i] : 0, wi = act ? e_ab[i] : ~0ull;
-                    // my side's absent balls must not equal the other side's
-                    const unsigned Ai = (unsigned)wi == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)wi;
-                    const unsigned Bi = (unsigned)(wi >> 32) == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)(wi >> 32);
-                    int rk = 0, fl = 0;
+                // as many lanes per key as one pass over the keys allows (PT / G keys per pass); G is a compile-time
+                // constant of the loop
+                auto rank_pass = [&](auto g_tag) {
+                    constexpr int G = decltype(g_tag)::value;
+                    const int c = pt & (G - 1);
+                    const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (lane & ~(G - 1));
+                    for (int i0 = (pt - lane) / G; i0 < nr; i0 += PT / G) {  // first entry of my warp: one trip count for its lanes
+                        const int i = i0 + lane / G;
+                        const bool act = i < nr;
+                        const uint64_t ti = act ? e_ts[i] : 0, ci = act ? e_code[i] : 0, wi = act ? e_ab[i] : ~0ull;
+                        // my side's absent balls must not equal the other side's
+                        const unsigned Ai = (unsigned)wi == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)wi;
+                        const unsigned Bi = (unsigned)(wi >> 32) == BL_NO_BALL ? BL_NO_BALL - 1 : (unsigned)(wi >> 32);
+                        int rk = 0, fl = 0;
 #pragma unroll 4
-                    for (int j = c; j < nr; j += G) {
-                        const uint64_t tj = e_ts[j], cj = e_code[j], wj = e_ab[j];
-                        const unsigned before = key_before_mask(tj, cj, (unsigned)j, ti, ci, (unsigned)i);
-                        const unsigned Aj = (unsigned)wj, Bj = (unsigned)(wj >> 32);
-                        const bool share = Aj == Ai || Aj == Bi || Bj == Ai || Bj == Bi;
-                        rk -= (int)before;
-                        fl |= (int)(before & (unsigned)(cj == ci ? F_DUP : (share ? F_CONFLICT : 0)));
+                        for (int j = c; j < nr; j += G) {
+                            const uint64_t tj = e_ts[j], cj = e_code[j], wj = e_ab[j];
+                            const unsigned before = key_before_mask(tj, cj, (unsigned)j, ti, ci, (unsigned)i);
+                            const unsigned Aj = (unsigned)wj, Bj = (unsigned)(wj >> 32);
+                            const bool share = Aj == Ai || Aj == Bi || Bj == Ai || Bj == Bi;
+                            rk -= (int)before;
+                            fl |= (int)(before & (unsigned)(cj == ci ? F_DUP : (share ? F_CONFLICT : 0)));
+                        }
+                        if (Ai == BL_NO_BALL - 1) fl = 0;  // a key without balls is neither
+                        if (G > 1) {
+                            rk = __reduce_add_sync(gmask, rk);
+                            fl = __reduce_or_sync(gmask, fl);
+                        }
+                        if (act && c == 0) { a_rank[i] = rk; a_flag[i] = fl; }
                     }
-                    if (Ai == BL_NO_BALL - 1) fl = 0;  // a key without balls is neither
-                    if (G > 1) {
-                        rk = __reduce_add_sync(gmask, rk);
-                        fl = __reduce_or_sync(gmask, fl);
-                    }
-                    if (act && c == 0) { a_rank[i] = rk; a_flag[i] = fl; }
-                }
+                };
+                if (PT >= 256) {
+                    if (nr * 8 <= PT) rank_pass(std::integral_constant<int, 8>());
+                    else rank_pass(std::integral_constant<int, 4>());
+                } else if (PT >= 128) rank_pass(std::integral_constant<int, 2>());
+                else rank_pass(std::integral_constant<int, 1>());
             }
             if (nwarps >= 2 && warp == rw) { const long long cq = clock64(); if (lane == 0) prof[12] += cq - cr0; }  // the first ranking warp's clock
         }
