@@ -57,7 +57,7 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
         return bl_check_cuda(h, e, "cudaMalloc");
     {
         const char *hz = getenv("BL_REPAIR_HORIZON");
-        h->repair_horizon = hz ? atof(hz) : 16.0;
+        h->repair_horizon = hz ? atof(hz) : 100.0;  // measured optimum 50-130 windows (profiles/r1_target_scan.log)
         const char *eg = getenv("BL_ENSEMBLE_GENERIC");
         h->ensemble_generic = eg ? atoi(eg) : 0;
     }

@@ -19,7 +19,7 @@ struct bl_handle {
     uint64_t *d_post;         // [2][BL_MAX_CTAS][BL_POST_WORDS] keys posted by each CTA
     uint64_t *d_stale;        // [BL_MAX_CTAS * BL_MAX_THREADS][2] candidates under repair
     uint64_t *d_partial;      // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
-    double repair_horizon;    // in windows (BL_REPAIR_HORIZON, default 8)
+    double repair_horizon;    // in windows (BL_REPAIR_HORIZON, default 100)
     // window length the last launch ended with, and the system it belongs to
     double window;
     int window_n;
