@@ -51,7 +51,9 @@
 // pair with a and the new value is larger, m[k] keeps the old time as a lower bound ("stale"); stale candidates
 // are made exact again only when they come near the front of the queue.  The global minimum over {m[k]} equals
 // the minimum over the whole table.
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "bl_arith.cuh"
@@ -88,6 +90,7 @@ struct Params {
     uint64_t *stale_list; // [BL_MAX_CTAS * BL_MAX_THREADS][2] (ball, seq) of the candidates under repair
     uint64_t *partial;    // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
     double repair_horizon; // stale candidates within this many windows of `now` are repaired together
+    double wc[5];          // window control: factor after a violation; growth factor, below this fraction of the target; shrink factor, above this fraction
 };
 
 // ---- shared memory map (8-byte words) -----------------------------------------------------------------
@@ -513,9 +516,9 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             }
             if (win > 0.0 && P.target > 1) mode = MODE_WINDOW;
         } else {
-            if (nc_ < nf_) win = bl_mul(win, 0.5);
-            else if (2 * nE_ < P.target) win = bl_mul(win, 1.5);
-            else if (nE_ > P.target + (P.target >> 1)) win = bl_mul(win, 0.75);
+            if (nc_ < nf_) win = bl_mul(win, P.wc[0]);
+            else if ((double)nE_ < P.wc[2] * P.target) win = bl_mul(win, P.wc[1]);
+            else if ((double)nE_ > P.wc[4] * P.target) win = bl_mul(win, P.wc[3]);
         }
     };
     // the last batch: committed optimistically, validated (and its rows stored) one barrier later
@@ -1371,12 +1374,10 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.result = h->d_result;
     P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
     P.m_max = pick_m_max(tb);
-    // Keys per round the window aims at (about half of them become collisions of the batch: the rest are the same pair
-    // posted twice, or lie behind the first conflict).  The chance that a round is cut short grows like m^2 / n, the
-    // synchronisation cost per collision falls like 1 / m; measured optimum on B200 ~ sqrt(n / 2) (N = 256: 12,
-    // 1024: 24, 2025: 32, 4096: 40-48, >= 8100: 52-60 -- profiles/r1_target_scan.log).
-    int target = 1;
-    while ((long long)(target + 1) * (target + 1) * 2 <= (long long)s->n) target++;
+    // Keys per round the window aims at.  The chance that a round is cut short grows like m^2 / n, the synchronisation
+    // cost per collision falls like 1 / m; measured optimum on B200 (profiles/r1_target_scan.log): N = 256: 12-14,
+    // 1024: 22-28, 4096: 36-40, >= 16384: 56-60, i.e. ~ 2.46 n^0.316.
+    int target = (int)(2.46 * pow((double)(s->n > 1 ? s->n : 1), 0.316) + 0.5);
     if (target > BL_SORT_CAP - 8) target = BL_SORT_CAP - 8;
     if (target > 2 * P.m_max) target = 2 * P.m_max;
     if (target < 1) target = 1;
@@ -1387,6 +1388,13 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.bar = h->d_bar; P.post = h->d_post;
     P.stale_list = h->d_stale; P.partial = h->d_partial;
     P.repair_horizon = h->repair_horizon;
+    {
+        // the window shrinks by 0.8 when a round was cut short by a violation, grows by 1.5 below half of the target,
+        // shrinks by 0.75 above 1.5 targets (a factor 0.5 after violations cost 2-5 %: profiles/r1_target_scan.log)
+        double wc[5] = {0.8, 1.5, 0.5, 0.75, 1.5};
+        if (const char *e = getenv("BL_WINCTL")) sscanf(e, "%lf,%lf,%lf,%lf,%lf", &wc[0], &wc[1], &wc[2], &wc[3], &wc[4]);
+        for (int q = 0; q < 5; q++) P.wc[q] = wc[q];
+    }
     size_t smem = (size_t)make_layout(P.Tb, P.H, P.m_max, s->n_obstacles).words * 8;
     if (smem > h->max_smem_optin)
         return bl_set_error(h, BL_EUNSUPPORTED, "event kernel needs %zu B of shared memory per CTA (limit %zu)", smem,
