@@ -1298,8 +1298,14 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, int *sync_mode) {
     *hh = 1;
     if (n <= 0) { *ncta = 1; *tb = 32; *sync_mode = SYNC_CTA; return BL_OK; }
-    if (n <= 64) { *ncta = 1; *tb = ((n + 31) / 32) * 32; *hh = n > 8 ? 4 : 1; *sync_mode = SYNC_CTA; return BL_OK; }
-    if (n <= 2048) {
+    if (n <= 64) {
+        *ncta = 1; *sync_mode = SYNC_CTA;
+        if (getenv("BL_SMALL_OLD")) { *tb = ((n + 31) / 32) * 32; *hh = n > 8 ? 4 : 1; }
+        else { *tb = 64; *hh = 8; }
+        return BL_OK;
+    }
+    const int cluster_max = getenv("BL_CLUSTER_MAX") ? atoi(getenv("BL_CLUSTER_MAX")) : 0;
+    if (n <= cluster_max) {
         int c = (n + 127) / 128;
         if (c < 2) c = 2;
         int p = 1;
@@ -1310,8 +1316,13 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
         *ncta = c; *tb = t; *hh = 4; *sync_mode = SYNC_CLUSTER;
         return BL_OK;
     }
-    int t = 128;
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    // medium systems: 64 balls per CTA with 8 threads each -- twice the CTAs, half the pair solves per thread
+    if (!getenv("BL_EVOLVE_TB128") && (n + 63) / 64 <= sms) {
+        *ncta = (n + 63) / 64; *tb = 64; *hh = 8; *sync_mode = SYNC_GRID;
+        return BL_OK;
+    }
+    int t = 128;
     while ((n + t - 1) / t > sms && t <= BL_MAX_THREADS) t += 32;
     if (t > BL_MAX_THREADS) return BL_EUNSUPPORTED;
     *ncta = (n + t - 1) / t; *tb = t; *sync_mode = SYNC_GRID;
@@ -1406,6 +1417,8 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     h->launches++;
     if (tb == 128 && hh == 4)
         return h->dot_fma ? launch_t<true, 512, 128, 4>(h, P, smem, st) : launch_t<false, 512, 128, 4>(h, P, smem, st);
+    if (tb == 64 && hh == 8)
+        return h->dot_fma ? launch_t<true, 512, 64, 8>(h, P, smem, st) : launch_t<false, 512, 64, 8>(h, P, smem, st);
     if (tb * hh <= 512)
         return h->dot_fma ? launch_t<true, 512, 0, 0>(h, P, smem, st) : launch_t<false, 512, 0, 0>(h, P, smem, st);
     return h->dot_fma ? launch_t<true, BL_MAX_THREADS, 0, 0>(h, P, smem, st)

@@ -37,7 +37,7 @@ def perturb():
 def long_run(target, n_events):
     h.check(h.lib.bl_set_batch_target(h.h, target))
     try:
-        bld = build(workloads.dense_gas(128))
+        bld = build(workloads.dense_gas(int(os.environ.get("DBG_SIDE", "128"))))
         t0 = time.perf_counter()
         counts, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
         torch.cuda.synchronize()
