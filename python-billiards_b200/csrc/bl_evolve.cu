@@ -42,8 +42,9 @@
 // sequence number says which of toi[i][j] / toi[j][i] is current (the row of the ball whose collision came
 // later) and bl_symmetrize makes both current again before anything on the host side reads the table.  The
 // kernel reads the table only to repair stale candidates.
-// Grid: ceil(N/Tb) CTAs, one per SM; <= 16 CTAs run as one thread-block cluster (hardware barrier), more use a
-// cooperative launch with a global-memory barrier.
+// Grid: ceil(N/Tb) CTAs, one per SM, cooperative launch with a global-memory barrier (64 balls x 8 threads up to 9472
+// balls, 128 x 4 above; launching <= 16 CTAs as one thread-block cluster with the hardware barrier is kept behind
+// BL_CLUSTER_MAX -- the 64 x 8 grid shape is faster at every size).
 //
 // "Cover" instead of row minima: ball k's candidate m[k] is the minimum over a SUBSET of row k that
 // always contains every pair whose value was last written at an event of the OTHER ball.  After an event of ball
@@ -1293,8 +1294,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// CTA shape: Tb balls per CTA, H threads per ball.  Up to 2048 balls run as one cluster of <= 16 CTAs (hardware
-// barrier); larger systems use one CTA of >= 128 balls per SM and a cooperative launch.
+// CTA shape: Tb balls per CTA, H threads per ball ("Grid").
 static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, int *sync_mode) {
     *hh = 1;
     if (n <= 0) { *ncta = 1; *tb = 32; *sync_mode = SYNC_CTA; return BL_OK; }
