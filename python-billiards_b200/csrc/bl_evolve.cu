@@ -1161,18 +1161,20 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             double *const q_b = wq + warp * (4 * BL_WQ_CAP), *const q_c = q_b + BL_WQ_CAP, *const q_d = q_c + BL_WQ_CAP;
             int *const q_dst = reinterpret_cast<int *>(q_d + BL_WQ_CAP);
             int qn = 0;
+            // my state as of just before the collision at hand: the state of record, after my own collision the new one
+            double sx = p0x, sy = p0y, svx = vx, svy = vy, st0 = t0;
+            int switch_after = myrank >= 0 ? myrank : 0x7fffffff;
             for (int r = h;; r += H) {
                 unsigned m0 = 0, m1 = 0;
                 bool hit0 = false, hit1 = false;
                 double b0 = 0, c0q = 0, d0 = 0, b1 = 0, c1q = 0, d1 = 0;
                 const bool last = r >= nf;
                 if (!last) {
+                    if (__any_sync(0xffffffffu, r > switch_after)) {  // rare: a ball of the batch passes its own collision
+                        if (r > switch_after) { sx = nx; sy = ny; svx = nvx; svy = nvy; st0 = nt0; switch_after = 0x7fffffff; }
+                    }
                     const double t = bt[2 * r];
                     const bool valid = own && r != myrank;  // not me / my partner in the same collision
-                    // my state as of just before that collision
-                    const bool after = myrank >= 0 && myrank < r;
-                    const double sx = after ? nx : p0x, sy = after ? ny : p0y, svx = after ? nvx : vx, svy = after ? nvy : vy;
-                    const double st0 = after ? nt0 : t0;
                     const double px = bl_advance(sx, svx, t, st0), py = bl_advance(sy, svy, t, st0);
                     const int x1 = bid[2 * r + 1];
                     if (qpart >= 0) {
