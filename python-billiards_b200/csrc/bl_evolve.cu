@@ -263,7 +263,8 @@ __host__ __device__ constexpr int pick_m_max(int tb) {
 // ---------------------------------------------------------------------------------------------
 // TB / HH > 0: balls per CTA and threads per ball fixed at compile time (the shape of the large systems), which turns
 // every shared-memory offset into an immediate; 0: taken from the launch parameters
-template <bool FMA, int MAXT, int TB, int HH>
+// KONE: all balls have the same radius (one radius class): (r1 + r2)**2 is one constant
+template <bool FMA, int MAXT, int TB, int HH, bool KONE = false>
 __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) uint64_t sm[];
     const bl_system &S = P.s;
@@ -1184,7 +1185,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     }
                     {
                         const int j = 2 * r;
-                        const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
+                        const double rs = (KONE || K == 1) ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
                         const double dpx = bl_sub(px, bx[j]), dpy = bl_sub(py, by[j]);
                         const double dvx = bl_sub(svx, bvx[j]), dvy = bl_sub(svy, bvy[j]);
                         b0 = bl_dot2<FMA>(dpx, dpy, dvx, dvy);
@@ -1195,7 +1196,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                     }
                     if (x1 >= 0) {
                         const int j = 2 * r + 1;
-                        const double rs = K == 1 ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
+                        const double rs = (KONE || K == 1) ? rs11 : __ldg(S.rsum2 + (size_t)brc[j] * K + myrc);
                         const double dpx = bl_sub(px, bx[j]), dpy = bl_sub(py, by[j]);
                         const double dvx = bl_sub(svx, bvx[j]), dvy = bl_sub(svy, bvy[j]);
                         b1 = bl_dot2<FMA>(dpx, dpy, dvx, dvy);
@@ -1339,9 +1340,9 @@ int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, in
     return rc;
 }
 
-template <bool FMA, int MAXT, int TB, int HH>
+template <bool FMA, int MAXT, int TB, int HH, bool KONE = false>
 static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
-    auto kern = bl_evolve_kernel<FMA, MAXT, TB, HH>;
+    auto kern = bl_evolve_kernel<FMA, MAXT, TB, HH, KONE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaFuncSetAttribute(smem)");
     const unsigned threads = (unsigned)(P.Tb * P.H);
@@ -1417,10 +1418,15 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     e = cudaMemsetAsync(h->d_bar, 0, 64, st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset barrier");
     h->launches++;
-    if (tb == 128 && hh == 4)
+    const bool kone = s->n_classes == 1;
+    if (tb == 128 && hh == 4) {
+        if (kone) return h->dot_fma ? launch_t<true, 512, 128, 4, true>(h, P, smem, st) : launch_t<false, 512, 128, 4, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 128, 4>(h, P, smem, st) : launch_t<false, 512, 128, 4>(h, P, smem, st);
-    if (tb == 64 && hh == 8)
+    }
+    if (tb == 64 && hh == 8) {
+        if (kone) return h->dot_fma ? launch_t<true, 512, 64, 8, true>(h, P, smem, st) : launch_t<false, 512, 64, 8, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 64, 8>(h, P, smem, st) : launch_t<false, 512, 64, 8>(h, P, smem, st);
+    }
     if (tb * hh <= 512)
         return h->dot_fma ? launch_t<true, 512, 0, 0>(h, P, smem, st) : launch_t<false, 512, 0, 0>(h, P, smem, st);
     return h->dot_fma ? launch_t<true, BL_MAX_THREADS, 0, 0>(h, P, smem, st)
