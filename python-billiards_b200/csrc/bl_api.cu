@@ -60,6 +60,14 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
         h->repair_horizon = hz ? atof(hz) : 100.0;  // measured optimum 50-130 windows (profiles/r1_target_scan.log)
         const char *eg = getenv("BL_ENSEMBLE_GENERIC");
         h->ensemble_generic = eg ? atoi(eg) : 0;
+        // the window shrinks by 0.8 when a round was cut short by a violation, grows by 1.5 below half of the target,
+        // shrinks by 0.75 above 1.5 targets (a factor 0.5 after violations cost 2-5 %: profiles/r1_target_scan.log)
+        const double wc[5] = {0.8, 1.5, 0.5, 0.75, 1.5};
+        for (int q = 0; q < 5; q++) h->winctl[q] = wc[q];
+        if (const char *w = getenv("BL_WINCTL"))
+            sscanf(w, "%lf,%lf,%lf,%lf,%lf", &h->winctl[0], &h->winctl[1], &h->winctl[2], &h->winctl[3], &h->winctl[4]);
+        const char *cm = getenv("BL_CLUSTER_MAX");
+        h->cluster_max = cm ? atoi(cm) : 0;
     }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");

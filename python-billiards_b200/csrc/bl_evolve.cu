@@ -111,7 +111,7 @@ struct Layout {
     int mts, mcode, ots;              // [Tb] candidate key, next-obstacle time (sortable)
     int sts, scode, lts, lcode;       // [Tb] second candidate; key that bounds the rest of the cover from below
     int seq;                          // [Tb] sequence number of the ball's last collision
-    int mass, radius, oarg;           // [Tb] doubles
+    int radius, oarg;                 // [Tb] doubles
     int oidx, brank, rclass;          // [Tb] ints (brank: [2][Tb])
     int undo;                         // [15][Tb] state before the optimistic commit of the last batch
     int bts;                          // [2][m_max] sortable collision times of the batch, by rank
@@ -145,7 +145,7 @@ __host__ __device__ inline Layout make_layout(int Tb, int H, int m_max, int n_ob
     L.mts = w; w += Tb; L.mcode = w; w += Tb; L.ots = w; w += Tb;
     L.sts = w; w += Tb; L.scode = w; w += Tb; L.lts = w; w += Tb; L.lcode = w; w += Tb;
     L.seq = w; w += Tb;
-    L.mass = w; w += Tb; L.radius = w; w += Tb; L.oarg = w; w += Tb;
+    L.radius = w; w += Tb; L.oarg = w; w += Tb;
     L.oidx = w; w += (Tb + 1) / 2; L.brank = w; w += Tb; L.rclass = w; w += (Tb + 1) / 2;
     L.undo = w; w += 15 * Tb;
     L.bts = w; w += 2 * m_max;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
     uint64_t *c_mts = sm + L.mts, *c_mcode = sm + L.mcode, *c_ots = sm + L.ots;
     uint64_t *c_sts = sm + L.sts, *c_scode = sm + L.scode, *c_lts = sm + L.lts, *c_lcode = sm + L.lcode;
     long long *c_seq = reinterpret_cast<long long *>(sm + L.seq);
-    double *c_mass = reinterpret_cast<double *>(sm + L.mass), *c_radius = reinterpret_cast<double *>(sm + L.radius);
+    double *c_radius = reinterpret_cast<double *>(sm + L.radius);
     double *c_oarg = reinterpret_cast<double *>(sm + L.oarg);
     int *c_oidx = reinterpret_cast<int *>(sm + L.oidx), *const brank_b = reinterpret_cast<int *>(sm + L.brank);
     uint64_t *const undo = sm + L.undo;  // [f][Tb], f = 0 mts, 1 mcode, 2..6 p0x p0y vx vy t0, 7 ots, 8 oarg, 9 oidx, 10 seq, 11..14 second candidate and bound
@@ -322,7 +322,6 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             st_p0x[bl] = S.p0x[k]; st_p0y[bl] = S.p0y[k]; st_vx[bl] = S.vx[k]; st_vy[bl] = S.vy[k]; st_t0[bl] = S.t0[k];
             c_seq[bl] = S.seq[k];
             c_rclass[bl] = S.rclass[k];
-            c_mass[bl] = S.mass[k];
             c_radius[bl] = S.radius[k];
             c_oarg[bl] = S.obs_arg[k];
             c_oidx[bl] = S.obs_idx[k];
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
             c_lcode[bl] = cc == BL_CODE_NONE ? BL_CODE_NONE : (cc == BL_CODE_STALE ? 0ull : cc + 1);
         } else {
             st_p0x[bl] = 0; st_p0y[bl] = 0; st_vx[bl] = 0; st_vy[bl] = 0; st_t0[bl] = 0;
-            c_seq[bl] = 0; c_rclass[bl] = 0; c_mass[bl] = 0; c_radius[bl] = 0; c_oarg[bl] = 0; c_oidx[bl] = -1;
+            c_seq[bl] = 0; c_rclass[bl] = 0; c_radius[bl] = 0; c_oarg[bl] = 0; c_oidx[bl] = -1;
             c_ots[bl] = ts_inf; c_mts[bl] = ts_inf; c_mcode[bl] = BL_CODE_NONE;
             c_sts[bl] = ts_inf; c_scode[bl] = BL_CODE_NONE; c_lts[bl] = ts_inf; c_lcode[bl] = BL_CODE_NONE;
         }
@@ -1303,12 +1302,10 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
     if (n <= 0) { *ncta = 1; *tb = 32; *sync_mode = SYNC_CTA; return BL_OK; }
     if (n <= 64) {
         *ncta = 1; *sync_mode = SYNC_CTA;
-        if (getenv("BL_SMALL_OLD")) { *tb = ((n + 31) / 32) * 32; *hh = n > 8 ? 4 : 1; }
-        else { *tb = 64; *hh = 8; }
+        *tb = 64; *hh = 8;
         return BL_OK;
     }
-    const int cluster_max = getenv("BL_CLUSTER_MAX") ? atoi(getenv("BL_CLUSTER_MAX")) : 0;
-    if (n <= cluster_max) {
+    if (n <= h->cluster_max) {
         int c = (n + 127) / 128;
         if (c < 2) c = 2;
         int p = 1;
@@ -1321,7 +1318,7 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
     }
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
     // medium systems: 64 balls per CTA with 8 threads each -- twice the CTAs, half the pair solves per thread
-    if (!getenv("BL_EVOLVE_TB128") && (n + 63) / 64 <= sms) {
+    if ((n + 63) / 64 <= sms) {
         *ncta = (n + 63) / 64; *tb = 64; *hh = 8; *sync_mode = SYNC_GRID;
         return BL_OK;
     }
@@ -1402,13 +1399,7 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     P.bar = h->d_bar; P.post = h->d_post;
     P.stale_list = h->d_stale; P.partial = h->d_partial;
     P.repair_horizon = h->repair_horizon;
-    {
-        // the window shrinks by 0.8 when a round was cut short by a violation, grows by 1.5 below half of the target,
-        // shrinks by 0.75 above 1.5 targets (a factor 0.5 after violations cost 2-5 %: profiles/r1_target_scan.log)
-        double wc[5] = {0.8, 1.5, 0.5, 0.75, 1.5};
-        if (const char *e = getenv("BL_WINCTL")) sscanf(e, "%lf,%lf,%lf,%lf,%lf", &wc[0], &wc[1], &wc[2], &wc[3], &wc[4]);
-        for (int q = 0; q < 5; q++) P.wc[q] = wc[q];
-    }
+    for (int q = 0; q < 5; q++) P.wc[q] = h->winctl[q];
     size_t smem = (size_t)make_layout(P.Tb, P.H, P.m_max, s->n_obstacles).words * 8;
     if (smem > h->max_smem_optin)
         return bl_set_error(h, BL_EUNSUPPORTED, "event kernel needs %zu B of shared memory per CTA (limit %zu)", smem,

@@ -20,6 +20,9 @@ struct bl_handle {
     uint64_t *d_stale;        // [BL_MAX_CTAS * BL_MAX_THREADS][2] candidates under repair
     uint64_t *d_partial;      // [2][BL_MAX_CTAS][BL_RCHUNK][2] per-CTA minima of a repair chunk
     double repair_horizon;    // in windows (BL_REPAIR_HORIZON, default 100)
+    double winctl[5];         // window control (BL_WINCTL): factor after a violation; growth factor, below this fraction
+                              // of the target; shrink factor, above this fraction
+    int cluster_max;          // systems up to this many balls launch as one thread-block cluster (BL_CLUSTER_MAX, default 0: never)
     // window length the last launch ended with, and the system it belongs to
     double window;
     int window_n;
