@@ -48,7 +48,7 @@ MEASURED_FP64_TFLOPS = 37.13
 # DRAM traffic of the two dominant kernels from their `ncu --set full` captures (profiles/r1_final_evolve_kernel_ncu_summary.md:
 # dram__bytes_read.sum + dram__bytes_write.sum = 1.841 GB + 5.043 GB for a 20 000-collision launch at N = 16384;
 # profiles/r1_ensemble_ncu_summary.md: 58.8 MB + 6.2 MB for 2^20 systems) -- scaled to the launch timed here
-NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 = (1.840679e9 + 5.043268e9) / 20000
+NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 = (1.947861e9 + 5.039994e9) / 20000
 NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.769408e6 + 6.243840e6) / (1 << 20)
 
 
@@ -187,7 +187,7 @@ def bench_gas(args, device, fma):
                 "traffic": (NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 * (n_bb + n_bo) / max(args.steps, 1)
                             if N == 16384 else None),
                 "traffic_source": "ncu --set full capture of a 20000-collision launch (profiles/), per collision, "
-                                  "scaled to this launch; row stores 252 KB + 92 KB read (stale-candidate repairs) per collision",
+                                  "scaled to this launch; row stores 252 KB + 97 KB read (stale-candidate repairs) per collision",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1),
                 "kernel_ms_per_launch": kernel_ms / max(args.steps, 1),
