@@ -49,7 +49,7 @@ MEASURED_FP64_TFLOPS = 37.13
 # dram__bytes_read.sum + dram__bytes_write.sum = 1.841 GB + 5.043 GB for a 20 000-collision launch at N = 16384;
 # profiles/r1_ensemble_ncu_summary.md: 58.8 MB + 6.2 MB for 2^20 systems) -- scaled to the launch timed here
 NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 = (1.947861e9 + 5.039994e9) / 20000
-NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.769408e6 + 6.243840e6) / (1 << 20)
+NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.758144e6 + 6.716928e6) / (1 << 20)
 
 
 def load_peaks():
