@@ -96,6 +96,26 @@ def test_host_argument_validation_needs_no_gpu():
     assert b.balls_position.tolist() == [[1.0, 2.0]] and b.balls_radius == [0.5] and b.balls_mass == [2.0]
 
 
+def test_queued_balls_mix_single_and_bulk_adds():
+    """add_ball / add_balls only queue (host mirrors grow, nothing touches the device until the first query): indices,
+    count and the mirrors follow the reference's add order; the queued chunks keep their own copies of the inputs."""
+    import billiards
+    b = billiards.Billiard()
+    assert b.add_ball((0, 0), (1, 0), 0.5) == 0
+    pos = np.array([[3.0, 0.0], [6.0, 1.0], [9.0, 2.0]])
+    vel = np.array([[0.0, 1.0], [0.0, 2.0], [0.0, 3.0]])
+    assert list(b.add_balls(pos, vel, radius=[0.1, 0.2, 0.1], mass=2.0)) == [1, 2, 3]
+    pos[:] = -1.0  # the caller's arrays are not aliased
+    assert b.add_ball((12, 3), (0, 4), 0.2, float("inf")) == 4
+    assert list(b.add_balls(np.zeros((0, 2)), np.zeros((0, 2)))) == [] and b.count == 5
+    assert b.balls_position.tolist() == [[0, 0], [3, 0], [6, 1], [9, 2], [12, 3]]
+    assert b.balls_velocity.tolist() == [[1, 0], [0, 1], [0, 2], [0, 3], [0, 4]]
+    assert b.balls_radius == [0.5, 0.1, 0.2, 0.1, 0.2] and b.balls_mass == [1.0, 2.0, 2.0, 2.0, float("inf")]
+    assert b._n_pending == 5 and sum(c[0].shape[0] for c in b._pending) == 5
+    queued = np.concatenate([c[0] for c in b._pending])
+    assert queued.tolist() == [[0, 0], [3, 0], [6, 1], [9, 2], [12, 3]]
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():
