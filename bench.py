@@ -417,7 +417,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gas-side", type=int, default=128, help="dense gas has side**2 balls (128 -> 16384)")
-    ap.add_argument("--events-per-step", type=int, default=100000)
+    ap.add_argument("--events-per-step", type=int, default=1000000,
+                    help="collisions per step; the default 10 steps are the 10^7 collisions of config D")
     ap.add_argument("--reference-events-per-step", type=int, default=10)
     ap.add_argument("--systems-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--collisions-per-system", type=int, default=10000)

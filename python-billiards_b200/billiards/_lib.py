@@ -90,6 +90,7 @@ SIGNATURES = {
     "bl_evolve_config": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "bl_set_batch_target": (ctypes.c_int, [_H, ctypes.c_int]),
     "bl_set_small_kernel": (ctypes.c_int, [_H, ctypes.c_int]),
+    "bl_set_cta_shape_limit": (ctypes.c_int, [_H, ctypes.c_int]),
 }
 
 _lib = None

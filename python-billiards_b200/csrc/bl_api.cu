@@ -24,6 +24,12 @@ int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what) {
 
 static cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 
+// largest system that runs 32 balls x 16 threads per CTA (bl_set_cta_shape_limit; BL_TB32_MAX overrides the default)
+static int default_tb32_max() {
+    const char *t32 = getenv("BL_TB32_MAX");
+    return t32 ? atoi(t32) : 2368;
+}
+
 extern "C" {
 
 const char *bl_version(void) { return "billiards_b200 0.1 (sm_100a)"; }
@@ -68,6 +74,7 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
             sscanf(w, "%lf,%lf,%lf,%lf,%lf", &h->winctl[0], &h->winctl[1], &h->winctl[2], &h->winctl[3], &h->winctl[4]);
         const char *cm = getenv("BL_CLUSTER_MAX");
         h->cluster_max = cm ? atoi(cm) : 0;
+        h->tb32_max = default_tb32_max();
     }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
@@ -262,6 +269,12 @@ int bl_evolve_config(const bl_handle *h, int n, int *ctas, int *threads) {
     if (!h || !ctas || !threads) return BL_EINVAL;
     int sync_mode;
     return bl_evolve_pick_config(h, n, ctas, threads, &sync_mode);
+}
+
+int bl_set_cta_shape_limit(bl_handle *h, int max_balls) {
+    if (!h) return BL_EINVAL;
+    h->tb32_max = max_balls < 0 ? default_tb32_max() : max_balls;
+    return BL_OK;
 }
 
 int bl_set_small_kernel(bl_handle *h, int enable) {

@@ -1317,6 +1317,12 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
         return BL_OK;
     }
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    // smaller systems: 32 balls per CTA with 16 threads each while that fills at most half of the chip (measured
+    // against 64 x 8: N=256 +9 %, 1024 +3 %, 2025 +3 %, 4096 +-0)
+    if (n <= h->tb32_max && (n + 31) / 32 <= sms) {
+        *ncta = (n + 31) / 32; *tb = 32; *hh = 16; *sync_mode = SYNC_GRID;
+        return BL_OK;
+    }
     // medium systems: 64 balls per CTA with 8 threads each -- twice the CTAs, half the pair solves per thread
     if ((n + 63) / 64 <= sms) {
         *ncta = (n + 63) / 64; *tb = 64; *hh = 8; *sync_mode = SYNC_GRID;
@@ -1413,6 +1419,10 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     if (tb == 128 && hh == 4) {
         if (kone) return h->dot_fma ? launch_t<true, 512, 128, 4, true>(h, P, smem, st) : launch_t<false, 512, 128, 4, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 128, 4>(h, P, smem, st) : launch_t<false, 512, 128, 4>(h, P, smem, st);
+    }
+    if (tb == 32 && hh == 16) {
+        if (kone) return h->dot_fma ? launch_t<true, 512, 32, 16, true>(h, P, smem, st) : launch_t<false, 512, 32, 16, true>(h, P, smem, st);
+        return h->dot_fma ? launch_t<true, 512, 32, 16>(h, P, smem, st) : launch_t<false, 512, 32, 16>(h, P, smem, st);
     }
     if (tb == 64 && hh == 8) {
         if (kone) return h->dot_fma ? launch_t<true, 512, 64, 8, true>(h, P, smem, st) : launch_t<false, 512, 64, 8, true>(h, P, smem, st);

@@ -146,7 +146,7 @@ def _oracle_log(oracle, cfg, fma, n_events):
     return ref, ref.log()
 
 
-@pytest.mark.parametrize("n_side,n_events", [(48, 4000), (128, 6000)])
+@pytest.mark.parametrize("n_side,n_events", [(48, 4000), (56, 2500), (128, 6000)])
 def test_grid_mode_long_run_against_oracle(billiards, oracle, n_side, n_events):
     """More than 2048 balls: cooperative grid launch, global-memory barrier, windows of dozens of collisions per
     round, several stale-candidate repair phases -- event by event against the CPU oracle."""
@@ -251,6 +251,47 @@ def test_stops_inside_a_batch(billiards, oracle):
     assert_bits_equal(a.balls_position, b.balls_position)
     assert_bits_equal(a.balls_velocity, b.balls_velocity)
     assert_bits_equal(np.concatenate(a.toi_table), np.concatenate(b.toi_table), "toi_table")
+
+
+def test_cta_shape_does_not_change_results(billiards, oracle):
+    """Systems of 65..2368 balls run 32 balls x 16 threads per CTA, larger ones 64 x 8: a speed choice only.  Both
+    shapes (one radius class and many) give the same log, state and table; the heterogeneous one also equals the
+    oracle event by event."""
+    from billiards import _lib
+    import ctypes
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+
+    def shape(n):
+        c, t = ctypes.c_int(), ctypes.c_int()
+        h.check(h.lib.bl_evolve_config(h.h, n, ctypes.byref(c), ctypes.byref(t)))
+        return c.value, t.value
+
+    hetero = workloads.hetero_gas(side=14, seed=11)
+    ref, (rt, ri, rj) = _oracle_log(oracle, hetero, fma, 3000)
+    for cfg, n_events in ((workloads.dense_gas(40, seed=5), 20000), (hetero, 3000), (workloads.dense_gas(9), 4000)):
+        runs = []
+        for limit in (-1, 0):
+            h.check(h.lib.bl_set_cta_shape_limit(h.h, limit))
+            try:
+                ctas = shape(cfg.n)[0]
+                bld = build(billiards, cfg, fma)
+                counts, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+                runs.append((ctas, counts, t, i, j, bld.balls_velocity.copy(), bld.balls_initial_position.copy(),
+                             np.concatenate(bld.toi_table)))
+            finally:
+                h.check(h.lib.bl_set_cta_shape_limit(h.h, -1))
+        a, b = runs
+        assert a[0] == (cfg.n + 31) // 32 and b[0] == (cfg.n + 63) // 64
+        assert a[1] == b[1] and sum(a[1]) == n_events
+        assert a[3].tolist() == b[3].tolist() and a[4].tolist() == b[4].tolist()
+        assert_bits_equal(a[2], b[2], "event times")
+        assert_bits_equal(a[5], b[5], "velocities")
+        assert_bits_equal(a[6], b[6], "initial positions")
+        assert_bits_equal(a[7], b[7], "toi_table")
+        if cfg is hetero:
+            assert a[3].tolist() == ri.tolist() and a[4].tolist() == rj.tolist()
+            assert_bits_equal(a[2], rt, "event times vs oracle")
 
 
 def test_batched_rounds_equal_one_at_a_time_over_a_long_run(billiards):
