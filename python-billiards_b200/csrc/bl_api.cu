@@ -27,7 +27,7 @@ static cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
 // largest system that runs 32 balls x 16 threads per CTA (bl_set_cta_shape_limit; BL_TB32_MAX overrides the default)
 static int default_tb32_max() {
     const char *t32 = getenv("BL_TB32_MAX");
-    return t32 ? atoi(t32) : 2368;
+    return t32 ? atoi(t32) : 3600;
 }
 
 extern "C" {

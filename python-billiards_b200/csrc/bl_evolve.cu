@@ -1317,8 +1317,8 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
         return BL_OK;
     }
     const int sms = h->sm_count > 0 ? h->sm_count : 148;
-    // smaller systems: 32 balls per CTA with 16 threads each while that fills at most half of the chip (measured
-    // against 64 x 8: N=256 +9 %, 1024 +3 %, 2025 +3 %, 4096 +-0)
+    // smaller systems: 32 balls per CTA with 16 threads each (measured against 64 x 8: N=100 +14 %, 256 +9 %,
+    // 1024 +3 %, 2025 +3 %, 3600 +1 %, 4096 +-0; profiles/r1_cta_shape_scan.log)
     if (n <= h->tb32_max && (n + 31) / 32 <= sms) {
         *ncta = (n + 31) / 32; *tb = 32; *hh = 16; *sync_mode = SYNC_GRID;
         return BL_OK;

@@ -23,7 +23,7 @@ struct bl_handle {
     double winctl[5];         // window control (BL_WINCTL): factor after a violation; growth factor, below this fraction
                               // of the target; shrink factor, above this fraction
     int cluster_max;          // systems up to this many balls launch as one thread-block cluster (BL_CLUSTER_MAX, default 0: never)
-    int tb32_max;             // systems of 65 .. this many balls run 32 balls x 16 threads per CTA (BL_TB32_MAX, default 2368 = 74 CTAs)
+    int tb32_max;             // systems of 65 .. this many balls run 32 balls x 16 threads per CTA (BL_TB32_MAX, default 3600: measured break-even near 4096)
     // window length the last launch ended with, and the system it belongs to
     double window;
     int window_n;

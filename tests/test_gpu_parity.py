@@ -146,7 +146,7 @@ def _oracle_log(oracle, cfg, fma, n_events):
     return ref, ref.log()
 
 
-@pytest.mark.parametrize("n_side,n_events", [(48, 4000), (56, 2500), (128, 6000)])
+@pytest.mark.parametrize("n_side,n_events", [(48, 4000), (64, 2500), (128, 6000)])
 def test_grid_mode_long_run_against_oracle(billiards, oracle, n_side, n_events):
     """More than 2048 balls: cooperative grid launch, global-memory barrier, windows of dozens of collisions per
     round, several stale-candidate repair phases -- event by event against the CPU oracle."""
@@ -254,7 +254,7 @@ def test_stops_inside_a_batch(billiards, oracle):
 
 
 def test_cta_shape_does_not_change_results(billiards, oracle):
-    """Systems of 65..2368 balls run 32 balls x 16 threads per CTA, larger ones 64 x 8: a speed choice only.  Both
+    """Systems of 65..3600 balls run 32 balls x 16 threads per CTA, larger ones 64 x 8: a speed choice only.  Both
     shapes (one radius class and many) give the same log, state and table; the heterogeneous one also equals the
     oracle event by event."""
     from billiards import _lib
@@ -611,6 +611,75 @@ def test_ensemble_kernel_variants(billiards, oracle):
     assert_bits_equal(ens.balls_velocity, want["v"])
     assert ens.hits.tolist() == want["hits"].tolist()
     assert int(ens.hits.sum()) == 96 * 70000
+
+
+def test_full_size_ideal_gas_two_schedules(billiards):
+    """Config I at its full size (BASELINE.json: N = 1024, 10^6 collisions), far beyond the oracle's reach: the default
+    schedule (32 x 16 CTAs, ~22 keys per round) against another decomposition of the same work (64 x 8 CTAs, 7 keys
+    per round) -- log digest, state and row minima bit for bit -- plus what the physics conserves."""
+    from billiards import _lib
+    import hashlib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.ideal_gas()
+    n_events = 10**6
+    runs = []
+    for limit, target in ((-1, 0), (0, 7)):
+        h.check(h.lib.bl_set_cta_shape_limit(h.h, limit))
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            counts, (t, i, j) = bld.evolve_events(n_events, log_capacity=n_events)
+        finally:
+            h.check(h.lib.bl_set_cta_shape_limit(h.h, -1))
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        assert sum(counts) == n_events and (np.diff(t) >= -1e-10).all()
+        digest = hashlib.sha256(t.tobytes() + i.tobytes() + j.tobytes()).hexdigest()
+        runs.append((counts, digest, bld.balls_velocity.copy(), bld.balls_position.copy(), bld._balls_toi.copy(),
+                     bld.time))
+    a, b = runs
+    assert a[0] == b[0] and a[1] == b[1] and a[5] == b[5]
+    assert_bits_equal(a[2], b[2], "velocities")
+    assert_bits_equal(a[3], b[3], "positions")
+    assert_bits_equal(a[4], b[4], "_balls_toi")
+    v, p, r = a[2], a[3], float(cfg.radius[0])
+    assert abs(float((v * v).sum()) / (cfg.n * 0.04) - 1.0) < 1e-9       # equal masses: sum |v|^2 is conserved
+    assert p.min() >= -1.0 + r - 1e-9 and p.max() <= 1.0 - r + 1e-9
+    d = p[:, None, :] - p[None, :, :]
+    gap = np.sqrt((d * d).sum(axis=2)) + 4.0 * np.eye(cfg.n)
+    assert gap.min() >= 2.0 * r - 1e-9, "overlapping balls"
+
+
+def test_full_size_sinai_ensemble_is_partition_invariant(billiards):
+    """Config S at its full size (2^20 systems x 10^4 collisions): one launch over all systems == two contiguous
+    shards (what two ranks would run) == the same shard in two launches of 5000; speeds stay 1, every ball stays
+    inside the box and outside the disk."""
+    from billiards import _lib
+    from billiards.ensemble import shard_bounds
+    fma = _lib.probe_dot_fma()
+    n, n_coll = 1 << 20, 10**4
+    obstacles, pos, vel = workloads.sinai(n, seed=1000)
+    obs = workloads.make_obstacles(billiards, obstacles)
+    whole = billiards.BilliardEnsemble(obs, pos, vel, dot_fma=fma, count_hits=True)
+    whole.run(n_coll)
+    t, p0, v = whole.time, whole.balls_initial_position, whole.balls_velocity
+    assert (whole.counts == n_coll).all()
+    stats = whole.gather_stats()
+    assert int(stats[0]) == n * n_coll == int(stats[1:].sum())
+    for rank in (0, 1):
+        lo, hi = shard_bounds(n, 2, rank)
+        part = billiards.BilliardEnsemble(obs, pos[lo:hi], vel[lo:hi], dot_fma=fma)
+        if rank == 0:
+            part.run(n_coll // 2)
+            part.run(n_coll - n_coll // 2)
+        else:
+            part.run(n_coll)
+        assert_bits_equal(part.time, t[lo:hi], f"shard {rank}: times")
+        assert_bits_equal(part.balls_initial_position, p0[lo:hi], f"shard {rank}: positions")
+        assert_bits_equal(part.balls_velocity, v[lo:hi], f"shard {rank}: velocities")
+    assert np.abs((v * v).sum(axis=1) - 1.0).max() < 1e-9
+    assert np.abs(p0).max() <= 1.0 + 1e-9 and (p0 * p0).sum(axis=1).min() >= 0.25 - 1e-9
+    assert (t > 0).all() and np.isfinite(t).all()
 
 
 def test_line_segments(billiards, golden, oracle):
