@@ -86,27 +86,27 @@ class BilliardEnsemble:
     @property
     def time(self):
         """time of the last collision of each system"""
-        return self._time.cpu().numpy()
+        return _lib.to_host(self._time)
 
     @property
     def counts(self):
-        return self._counts.cpu().numpy()
+        return _lib.to_host(self._counts)
 
     @property
     def hits(self):
-        return None if self._hits is None else self._hits.cpu().numpy().T
+        return None if self._hits is None else _lib.to_host(self._hits).T
 
     @property
     def balls_initial_position(self):
-        return self._state[0:2].T.contiguous().cpu().numpy()  # transposed on the device, one copy of what is asked for
+        return _lib.to_host(self._state[0:2].T.contiguous())  # transposed on the device, one copy of what is asked for
 
     @property
     def balls_velocity(self):
-        return self._state[2:4].T.contiguous().cpu().numpy()
+        return _lib.to_host(self._state[2:4].T.contiguous())
 
     def positions_at(self, time):
         """ball positions at a common ``time`` (p0 + v*(time - t0), valid until each system's next collision)"""
-        s = self._state.cpu().numpy()
+        s = _lib.to_host(self._state)
         dt = float(time) - s[4]
         return np.stack([s[0] + s[2] * dt, s[1] + s[3] * dt], axis=1)
 
