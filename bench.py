@@ -47,9 +47,9 @@ SM_COUNT, FP64_LANES_PER_SM = 148, 64
 MEASURED_FP64_TFLOPS = 37.13
 # DRAM traffic of the two dominant kernels from their `ncu --set full` captures (profiles/r1_final_evolve_kernel_ncu_summary.md:
 # dram__bytes_read.sum + dram__bytes_write.sum = 1.841 GB + 5.043 GB for a 20 000-collision launch at N = 16384;
-# profiles/r1_ensemble_ncu_summary.md: 58.8 MB + 6.2 MB for 2^20 systems) -- scaled to the launch timed here
+# profiles/r1_final_ensemble_ncu_summary.md: 58.8 MB + 8.0 MB for 2^20 systems) -- scaled to the launch timed here
 NCU_EVOLVE_DRAM_BYTES_PER_COLLISION_16384 = (1.947861e9 + 5.039994e9) / 20000
-NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.758144e6 + 6.716928e6) / (1 << 20)
+NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM = (58.755840e6 + 8.023552e6) / (1 << 20)
 
 
 def load_peaks():
@@ -295,7 +295,7 @@ def bench_ensemble(args, device, fma, rank, world, steps, warmup):
     roofline = {"kernel": "bl_ensemble_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": NCU_ENSEMBLE_DRAM_BYTES_PER_SYSTEM * n_local,
-                "traffic_source": "ncu --set full capture (profiles/r1_ensemble_ncu_summary.md): state load + store only",
+                "traffic_source": "ncu --set full capture (profiles/r1_final_ensemble_ncu_summary.md): state load + store only",
                 "peak_source": "measured DFMA peak, tools/microbench.cu (profiles/r1_microbench.log); equals "
                                "148 SM x 64 lanes x 2 x 1.96 GHz",
                 "algorithmic_flops_per_collision": FP64_FLOPS_PER_SINAI_COLLISION,
