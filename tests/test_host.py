@@ -182,3 +182,50 @@ def test_ensemble_sharding_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "gloo ok" in res.stdout
+
+
+def test_api_surface_matches_the_reference():
+    """Drop-in boundary: every public class, method, property, function and parameter of the reference's
+    hot-path modules exists here with the same name, kind and default -- recorded from the live reference by
+    tests/golden/make_api_surface.py.  Extra trailing keyword parameters (device=, dot_fma=) are allowed."""
+    import inspect
+    import json
+    import billiards
+    with open(os.path.join(ROOT, "tests", "golden", "api_surface.json")) as f:
+        want = json.load(f)
+
+    def check(fn, params, where):
+        have = [[p.name, p.kind.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                for p in inspect.signature(fn).parameters.values()]
+        assert have[:len(params)] == params, f"{where}: {have} vs reference {params}"
+        for extra in have[len(params):]:
+            assert extra[2] is not None or extra[1].startswith("VAR_"), f"{where}: extra parameter {extra} has no default"
+
+    def check_class(cls, spec, where):
+        for name, params in spec["methods"].items():
+            check(getattr(cls, name), params, f"{where}.{name}")
+        for name in spec["properties"]:
+            assert isinstance(inspect.getattr_static(cls, name), property), f"{where}.{name} is not a property"
+
+    for name in want["package"]:
+        assert hasattr(billiards, name), name
+    check_class(billiards.simulation.Billiard, want["simulation.Billiard"], "Billiard")
+    for cls, spec in want["obstacles"].items():
+        check_class(getattr(billiards.obstacles, cls), spec, cls)
+        assert issubclass(getattr(billiards.obstacles, cls), billiards.obstacles.Obstacle)
+    for name, params in want["physics"].items():
+        check(getattr(billiards.physics, name), params, f"physics.{name}")
+    b = billiards.Billiard()
+    b.add_ball((1, 2), (3, 4), 0.5, 2.0)
+    for attr in want["Billiard.attributes"]:
+        if attr != "toi_table":            # needs the device
+            assert hasattr(b, attr), attr
+    assert isinstance(inspect.getattr_static(billiards.Billiard, "toi_table"), property) or hasattr(b, "toi_table")
+
+
+def test_to_host_passes_cpu_tensors_through():
+    import torch
+    from billiards import _lib
+    t = torch.arange(6, dtype=torch.float64).reshape(3, 2)
+    out = _lib.to_host(t)
+    assert isinstance(out, np.ndarray) and out.tolist() == t.tolist()
