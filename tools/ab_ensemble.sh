@@ -10,7 +10,6 @@
 set -e
 cd "$(dirname "$0")/.."
 CSRC=python-billiards_b200/csrc
-LIB=python-billiards_b200/billiards/libbilliards_b200.so
 if [ "$1" = build ]; then
     mkdir -p tools/bin
     cp "$3" $CSRC/_variant_$2.cu
@@ -24,8 +23,7 @@ elif [ "$1" = run ]; then
     shift
     python tools/ensemble_crosscheck.py run /tmp/ab_base.npz 1048576 10000
     for v in "$@"; do
-        cp tools/bin/lib_$v.so $LIB
-        python tools/ensemble_crosscheck.py run /tmp/ab_$v.npz 1048576 10000
+        BILLIARDS_B200_LIB=$PWD/tools/bin/lib_$v.so python tools/ensemble_crosscheck.py run /tmp/ab_$v.npz 1048576 10000
         echo "$v vs in-tree: $(python tools/ensemble_crosscheck.py compare /tmp/ab_$v.npz /tmp/ab_base.npz | tr '\n' ' ')"
     done
 else
