@@ -624,8 +624,12 @@ int orc_segment_resolve(int dot_fma, const double *sg, const double *pos, const 
  * (simulation.py:504-554 with N = 1) starting from time 0.  state: [n_sys][4] = px,py,vx,vy in,
  * p0x,p0y,vx,vy out (position at the last collision); t_out[n_sys] = time of the last collision;
  * hits[n_sys][nobs] optional per-obstacle hit counters. */
-int orc_ensemble_run(int dot_fma, const orc_obstacle *obs, int nobs, long long n_sys, double radius,
-                     double *state, double *t_out, long long n_coll, long long *done, int32_t *hits) {
+/* status != NULL: a system whose collision cannot be resolved (ORC_ESEPARATING / ORC_EDIVZERO: the reference would
+ * raise inside bounce_ball_obstacle, after _move) stops there -- clock at the failed collision, state of record
+ * untouched -- and the other systems carry on; status == NULL: the first such error is returned. */
+int orc_ensemble_run2(int dot_fma, const orc_obstacle *obs, int nobs, long long n_sys, double radius,
+                      double *state, double *t_out, long long n_coll, long long *done, int32_t *hits,
+                      int32_t *status) {
     orc_billiard o; memset(&o, 0, sizeof(o)); o.dot_fma = dot_fma;
     for (long long s = 0; s < n_sys; s++) {
         double p0[2] = {state[4 * s], state[4 * s + 1]}, v[2] = {state[4 * s + 2], state[4 * s + 3]};
@@ -644,7 +648,11 @@ int orc_ensemble_run(int dot_fma, const orc_obstacle *obs, int nobs, long long n
             time = tn;
             double w[2];
             int st = obstacle_resolve(&o, &obs[q_min], pos, v, arg_min, w);
-            if (st != ORC_OK) return st;
+            if (st != ORC_OK) {
+                if (!status) return st;
+                status[s] = st;
+                break;
+            }
             t0 = time; p0[0] = pos[0]; p0[1] = pos[1]; v[0] = w[0]; v[1] = w[1];
             if (hits) hits[s * nobs + q_min]++;
         }
@@ -653,4 +661,9 @@ int orc_ensemble_run(int dot_fma, const orc_obstacle *obs, int nobs, long long n
         if (done) done[s] = c;
     }
     return ORC_OK;
+}
+
+int orc_ensemble_run(int dot_fma, const orc_obstacle *obs, int nobs, long long n_sys, double radius,
+                     double *state, double *t_out, long long n_coll, long long *done, int32_t *hits) {
+    return orc_ensemble_run2(dot_fma, obs, nobs, n_sys, radius, state, t_out, n_coll, done, hits, NULL);
 }

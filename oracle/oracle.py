@@ -93,6 +93,7 @@ def lib():
         L.orc_ensemble_run.argtypes = [ctypes.c_int, ctypes.POINTER(_Obstacle), ctypes.c_int, ctypes.c_longlong,
                                        ctypes.c_double, dp, dp, ctypes.c_longlong,
                                        ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int32)]
+        L.orc_ensemble_run2.argtypes = L.orc_ensemble_run.argtypes + [ctypes.POINTER(ctypes.c_int32)]
         _LIB = L
     return _LIB
 
@@ -361,8 +362,10 @@ def segment_resolve(segment, pos, vel, u, dot_fma=True):
     return w
 
 
-def ensemble_run(obstacles, pos, vel, n_collisions, radius=0.0, dot_fma=True, count_hits=False):
-    """Config S: every system = one ball + the shared obstacles; n_collisions x bounce_ball_obstacle()."""
+def ensemble_run(obstacles, pos, vel, n_collisions, radius=0.0, dot_fma=True, count_hits=False, per_system_status=False):
+    """Config S: every system = one ball + the shared obstacles; n_collisions x bounce_ball_obstacle().
+    ``per_system_status``: a system whose collision cannot be resolved stops there (``out["status"]``), the others
+    carry on; otherwise the first such error raises."""
     pos = np.asarray(pos, dtype=np.float64)
     vel = np.asarray(vel, dtype=np.float64)
     n_sys = pos.shape[0]
@@ -378,12 +381,16 @@ def ensemble_run(obstacles, pos, vel, n_collisions, radius=0.0, dot_fma=True, co
     t_out = np.empty(n_sys)
     done = np.zeros(n_sys, dtype=np.int64)
     hits = np.zeros((n_sys, len(obstacles)), dtype=np.int32) if count_hits else None
-    st = lib().orc_ensemble_run(int(bool(dot_fma)), obs, len(obstacles), n_sys, float(radius), _dp(state), _dp(t_out),
-                                int(n_collisions), done.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
-                                None if hits is None else hits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    status = np.zeros(n_sys, dtype=np.int32) if per_system_status else None
+    st = lib().orc_ensemble_run2(int(bool(dot_fma)), obs, len(obstacles), n_sys, float(radius), _dp(state), _dp(t_out),
+                                 int(n_collisions), done.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                 None if hits is None else hits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                 None if status is None else status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
     if st:
         raise OracleError(st)
     out = {"p0": state[:, :2].copy(), "v": state[:, 2:].copy(), "t": t_out, "done": done}
+    if status is not None:
+        out["status"] = status
     if hits is not None:
         out["hits"] = hits
     return out

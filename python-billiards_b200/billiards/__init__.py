@@ -13,9 +13,15 @@ hand-written sm_100a kernels in ``libbilliards_b200.so`` (C ABI: ``include/billi
 package does not need a GPU, using it does -- there is no CPU fallback.
 """
 
+from collections import namedtuple as _namedtuple
+
+from . import obstacles, physics, simulation
 from .ensemble import BilliardEnsemble
 from .obstacles import Disk, InfiniteWall, LineSegment, Obstacle
 from .simulation import Billiard
 
 __version__ = "1.0.0.dev0+b200"
-__all__ = ["Billiard", "BilliardEnsemble", "Disk", "InfiniteWall", "LineSegment", "Obstacle"]
+# same shape as the reference's tuple (__init__.py:31-66 there): (major, minor, micro, releaselevel, serial)
+__version__info__ = _namedtuple("VersionInfo", ["major", "minor", "micro", "releaselevel", "serial"])(1, 0, 0, "dev", 0)
+__all__ = ["obstacles", "physics", "simulation", "Billiard", "BilliardEnsemble", "Disk", "InfiniteWall", "LineSegment",
+           "Obstacle"]

@@ -49,6 +49,15 @@ class BlResult(ctypes.Structure):
                 ("err_j", ctypes.c_int64), ("prof", ctypes.c_int64 * 16), ("window", ctypes.c_double)]
 
 
+class BlMulti(ctypes.Structure):
+    _fields_ = [("n_sys", ctypes.c_int64), ("n", ctypes.c_int32), ("n_classes", ctypes.c_int32),
+                ("n_obstacles", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("p0x", c_void), ("p0y", c_void), ("vx", c_void), ("vy", c_void), ("t0", c_void),
+                ("radius", c_void), ("mass", c_void), ("rclass", c_void), ("rsum2", c_void), ("rsum2_obs", c_void),
+                ("obstacles", c_void), ("toi", c_void), ("obs_t", c_void), ("obs_arg", c_void), ("obs_idx", c_void),
+                ("time", c_void), ("n_ball_ball", c_void), ("n_ball_obstacle", c_void), ("status", c_void)]
+
+
 class BlLog(ctypes.Structure):
     _fields_ = [("cap", ctypes.c_int64), ("t", c_void), ("i", c_void), ("j", c_void), ("payload", c_void)]
 
@@ -85,9 +94,14 @@ SIGNATURES = {
                                        ctypes.c_int64, c_void, c_void, ctypes.c_int64, ctypes.c_double, c_void, c_void,
                                        c_void, c_void]),
     "bl_ensemble_stats": (ctypes.c_int, [_H, c_void, c_void, ctypes.c_int, ctypes.c_int64, c_void, c_void]),
+    "bl_selftest_div2": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), c_double_p,
+                                        c_void]),
+    "bl_multi_run": (ctypes.c_int, [_H, ctypes.POINTER(BlMulti), ctypes.c_int, ctypes.c_double, ctypes.c_int64, c_void]),
+    "bl_multi_positions": (ctypes.c_int, [_H, ctypes.POINTER(BlMulti), ctypes.c_double, ctypes.c_int, c_void, c_void]),
     "bl_last_kernel_ms": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_float)]),
     "bl_launch_count": (ctypes.c_int64, [_H]),
     "bl_evolve_config": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "bl_set_ensemble_generic": (ctypes.c_int, [_H, ctypes.c_int]),
     "bl_set_batch_target": (ctypes.c_int, [_H, ctypes.c_int]),
     "bl_set_small_kernel": (ctypes.c_int, [_H, ctypes.c_int]),
     "bl_set_cta_shape_limit": (ctypes.c_int, [_H, ctypes.c_int]),

@@ -1,11 +1,19 @@
-"""``BilliardEnsemble``: many independent single-ball billiards sharing one obstacle list.
+"""``BilliardEnsemble``: many independent billiards sharing one obstacle list.
 
 The reference has no ensemble type -- ``examples/sinai_billiard.py:33-38`` fakes one by putting non-interacting
-point particles into a single ``Billiard`` (and ``Notes.md:14`` wishes for a ``ParticleBilliard``).  Here every
-system is exactly "a ``Billiard`` with one ball" stepped with ``bounce_ball_obstacle()``
-(simulation.py:504-554), one CUDA thread per system (``bl_ensemble_run``).  Systems are independent, so an
-ensemble shards over GPUs with no exchange during the run; ``torch.distributed`` (NCCL over NVLink) is used only
-to gather the final statistics.
+point particles into a single ``Billiard`` (and ``Notes.md:14`` wishes for a ``ParticleBilliard``).  Two shapes:
+
+* **one ball per system** (``pos`` of shape ``(S, 2)``; config S of BASELINE.json): every system is exactly "a
+  ``Billiard`` with one ball" stepped with ``bounce_ball_obstacle()`` (simulation.py:504-554), one CUDA thread per
+  system (``bl_ensemble_run``);
+* **n <= 32 balls per system** (``pos`` of shape ``(S, n, 2)``; e.g. 2^16 pool tables with different break shots): every
+  system is exactly "a ``Billiard`` with these n balls" run with ``evolve`` (simulation.py:354-438), W = 2..32 lanes of
+  a warp per system with the system's time-of-impact table in shared memory (``bl_multi_run``) -- the same kernel
+  that serves a single small ``Billiard``, so system s of the ensemble and a ``Billiard`` built from the same numbers
+  agree bit for bit.  Radii and masses are per ball slot, the same in every system.
+
+Systems are independent, so an ensemble shards over GPUs with no exchange during the run (``shard_bounds``);
+``torch.distributed`` (NCCL over NVLink) is used only to gather the final statistics.
 """
 
 import ctypes
@@ -25,18 +33,25 @@ def shard_bounds(n_total, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _as_f64_tensor(x):
+    import torch
+    return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+
+
 class BilliardEnsemble:
-    """n independent systems: obstacles + ONE ball each (same radius for all), all starting at time 0.
+    """S independent systems: the obstacles + one ball each (``pos`` (S, 2)) or n <= 32 balls each (``pos`` (S, n, 2)),
+    all starting at time 0.
 
     Args:
-        obstacles: list of ``Disk`` / ``InfiniteWall`` (list order breaks ties, as in ``Billiard``).
-        pos, vel: arrays (n, 2) -- initial position and velocity of each system's ball.
-        radius: ball radius (0 = point particle).
+        obstacles: list of ``Disk`` / ``InfiniteWall`` / ``LineSegment`` (list order breaks ties, as in ``Billiard``).
+        pos, vel: initial positions and velocities, numpy arrays or (pinned) torch CPU tensors.
+        radius: ball radius (0 = point particle); per ball slot (n,) for multi-ball systems.
+        mass: per ball slot (n,) for multi-ball systems (a single ball never needs one).
         device, dot_fma: as for ``Billiard``.
-        count_hits: keep per-obstacle hit counters.
+        count_hits: keep per-obstacle hit counters (one-ball systems).
     """
 
-    def __init__(self, obstacles, pos, vel, radius=0.0, device=None, dot_fma=None, count_hits=False):
+    def __init__(self, obstacles, pos, vel, radius=0.0, mass=1.0, device=None, dot_fma=None, count_hits=False):
         import torch
         self.obstacles = list(obstacles)
         for obs in self.obstacles:
@@ -44,21 +59,24 @@ class BilliardEnsemble:
                 raise TypeError(f"{obs} must be an obstacle.Obstacle instance")
         self._records = [o._device_record() for o in self.obstacles]
         self._rec_array = (_lib.BlObstacle * max(len(self._records), 1))(*self._records)
+        pos_t, vel_t = _as_f64_tensor(pos), _as_f64_tensor(vel)
+        if pos_t.shape != vel_t.shape or pos_t.dtype != torch.float64 or vel_t.dtype != torch.float64 \
+                or pos_t.dim() not in (2, 3) or pos_t.shape[-1] != 2:
+            raise ValueError(f"pos and vel must be float64 arrays of the same shape (S, 2) or (S, n, 2), got "
+                             f"{tuple(pos_t.shape)} and {tuple(vel_t.shape)}")
+        self._handle = _lib.get_handle(device, dot_fma)
+        self.n = pos_t.shape[0]
+        self.balls_per_system = 1 if pos_t.dim() == 2 else int(pos_t.shape[1])
+        self._multi = pos_t.dim() == 3
+        if self._multi:
+            self._init_multi(pos_t, vel_t, radius, mass)
+            return
+        dev = self._handle.torch_device
         self.radius = float(radius)
         # (R + r)**2 with Python floats, like Disk.detect_collision -> toi_ball_ball does (physics.py:52)
         self._rsum2 = np.asarray([float((o.radius + self.radius) ** 2) if r.kind == _lib.BL_OBS_DISK else
                                   float(self.radius ** 2) if r.kind == _lib.BL_OBS_SEGMENT else 0.0
                                   for o, r in zip(self.obstacles, self._records)] or [0.0], dtype=np.float64)
-        # numpy arrays or (pinned) torch CPU tensors of shape (n, 2); the H2D copy is asynchronous for pinned input
-        pos_t = pos if isinstance(pos, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64))
-        vel_t = vel if isinstance(vel, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(vel, dtype=np.float64))
-        pos_t, vel_t = pos_t.reshape(-1, 2), vel_t.reshape(-1, 2)
-        if pos_t.shape != vel_t.shape or pos_t.dtype != torch.float64 or vel_t.dtype != torch.float64:
-            raise ValueError(f"pos and vel must be float64 arrays of the same shape, got {tuple(pos_t.shape)} and "
-                             f"{tuple(vel_t.shape)}")
-        self.n = pos_t.shape[0]
-        self._handle = _lib.get_handle(device, dot_fma)
-        dev = self._handle.torch_device
         self._state = torch.zeros((5, self.n), dtype=torch.float64, device=dev)  # SoA: p0x p0y vx vy t0
         self._state[0:2].copy_(pos_t.to(dev, non_blocking=True).T)
         self._state[2:4].copy_(vel_t.to(dev, non_blocking=True).T)
@@ -67,10 +85,104 @@ class BilliardEnsemble:
         self._status = torch.zeros(self.n, dtype=torch.int32, device=dev)
         self._hits = torch.zeros((len(self.obstacles), self.n), dtype=torch.int32, device=dev) if count_hits else None
 
-    # -- stepping ------------------------------------------------------------------------------------
-    def run(self, n_collisions, end_time=INF, sync=True):
-        """Every system handles its next ``n_collisions`` collisions (or stops at ``end_time``)."""
+    # ================================================================================================
+    # n balls per system
+    # ================================================================================================
+    def _init_multi(self, pos_t, vel_t, radius, mass):
         import torch
+        h = self._handle
+        dev = h.torch_device
+        S, n = self.n, self.balls_per_system
+        if not 1 <= n <= 32:
+            raise ValueError(f"multi-ball ensembles hold 1..32 balls per system, got {n} "
+                             "(larger systems are single Billiards: the grid-wide event kernel)")
+        self.balls_radius = [float(x) for x in np.broadcast_to(np.asarray(radius, dtype=np.float64), (n,))]
+        self.balls_mass = [float(x) for x in np.broadcast_to(np.asarray(mass, dtype=np.float64), (n,))]
+        classes, class_radii = {}, []
+        for r in self.balls_radius:
+            if r not in classes:
+                classes[r] = len(class_radii)
+                class_radii.append(r)
+        disk_r = [float(o.radius) if rec.kind == _lib.BL_OBS_DISK else 0.0
+                  for o, rec in zip(self.obstacles, self._records)]
+        rs, rs_obs = _lib.pow2_table(class_radii, disk_r)  # libm pow, like float.__pow__ (physics.py:52)
+        for q, rec in enumerate(self._records):
+            if rec.kind == _lib.BL_OBS_WALL:
+                rs_obs[q, :] = 0.0
+        d = {}
+        d["rsum2"] = torch.from_numpy(rs).to(dev)
+        d["rsum2_obs"] = torch.from_numpy(np.ascontiguousarray(rs_obs).reshape(-1)).to(dev) if rs_obs.size \
+            else torch.zeros(1, dtype=torch.float64, device=dev)
+        d["obstacles"] = torch.from_numpy(np.frombuffer(bytes(self._rec_array), dtype=np.uint8).copy()).to(dev)
+        d["radius"] = torch.tensor(self.balls_radius, dtype=torch.float64, device=dev)
+        d["mass"] = torch.tensor(self.balls_mass, dtype=torch.float64, device=dev)
+        d["rclass"] = torch.tensor([classes[r] for r in self.balls_radius], dtype=torch.int32, device=dev)
+        # state of record, SoA over (system, ball): one H2D copy each for pos and vel, de-interleaved on the device
+        p = pos_t.to(dev, non_blocking=True)
+        v = vel_t.to(dev, non_blocking=True)
+        d["p0x"], d["p0y"] = p[..., 0].contiguous(), p[..., 1].contiguous()
+        d["vx"], d["vy"] = v[..., 0].contiguous(), v[..., 1].contiguous()
+        d["t0"] = torch.zeros((S, n), dtype=torch.float64, device=dev)
+        d["toi"] = torch.empty((S, n, n), dtype=torch.float64, device=dev)
+        d["obs_t"] = torch.empty((S, n), dtype=torch.float64, device=dev)
+        d["obs_arg"] = torch.empty((S, n), dtype=torch.float64, device=dev)
+        d["obs_idx"] = torch.empty((S, n), dtype=torch.int32, device=dev)
+        d["time"] = torch.zeros(S, dtype=torch.float64, device=dev)
+        d["n_ball_ball"] = torch.zeros(S, dtype=torch.int64, device=dev)
+        d["n_ball_obstacle"] = torch.zeros(S, dtype=torch.int64, device=dev)
+        d["status"] = torch.zeros(S, dtype=torch.int32, device=dev)
+        self._dev = d
+        self._n_classes = len(class_radii)
+        self._fresh = True  # tables not built yet: the first run solves every pair at time 0, like add_ball
+        self._hits = None
+
+    def _multi_struct(self):
+        m = _lib.BlMulti()
+        m.n_sys, m.n, m.n_classes, m.n_obstacles = self.n, self.balls_per_system, self._n_classes, len(self.obstacles)
+        for name in ("p0x", "p0y", "vx", "vy", "t0", "radius", "mass", "rclass", "rsum2", "rsum2_obs", "obstacles",
+                     "toi", "obs_t", "obs_arg", "obs_idx", "time", "n_ball_ball", "n_ball_obstacle", "status"):
+            setattr(m, name, self._dev[name].data_ptr())
+        return m
+
+    def _run_multi(self, n_collisions, end_time, sync):
+        import torch
+        h = self._handle
+        m = self._multi_struct()
+        h.check(h.lib.bl_multi_run(h.h, ctypes.byref(m), int(self._fresh), float(end_time), int(n_collisions),
+                                   h.stream()))
+        self._fresh = False
+        if sync:
+            torch.cuda.current_stream(h.torch_device).synchronize()
+            st = self._dev["status"]
+            bad = int((st != 0).sum().item())
+            if bad:
+                first = int(torch.nonzero(st)[0].item())
+                code = int(st[first].item())
+                what = {_lib.BL_ESEPARATING: "balls are not moving towards each other (ValueError in the reference)",
+                        _lib.BL_EDIVZERO: "two zero-mass balls collided (divide by zero)",
+                        _lib.BL_ENAN: "a NaN impact time"}.get(code, f"status {code}")
+                raise ValueError(f"{bad} systems stopped early, first: system {first}: {what}")
+
+    def evolve(self, end_time):
+        """Every system runs ``Billiard.evolve(end_time)``; returns the (ball-ball, ball-obstacle) collision counts of
+        this call per system as two int64 arrays."""
+        if not self._multi:
+            raise TypeError("evolve(end_time) is for multi-ball ensembles; one-ball ensembles use run()")
+        before_bb, before_bo = self._dev["n_ball_ball"].clone(), self._dev["n_ball_obstacle"].clone()
+        self._run_multi(-1, end_time, True)
+        return (_lib.to_host(self._dev["n_ball_ball"] - before_bb), _lib.to_host(self._dev["n_ball_obstacle"] - before_bo))
+
+    # ================================================================================================
+    # stepping
+    # ================================================================================================
+    def run(self, n_collisions, end_time=INF, sync=True):
+        """Every system handles its next ``n_collisions`` collisions (or stops at ``end_time``; ``n_collisions`` < 0 =
+        no limit on the count)."""
+        import torch
+        if end_time != end_time:
+            raise ValueError("end_time must not be NaN")
+        if self._multi:
+            return self._run_multi(n_collisions, end_time, sync)
         h = self._handle
         h.check(h.lib.bl_ensemble_run(
             h.h, self._rec_array, len(self._records), self._rsum2.ctypes.data_as(_lib.c_double_p), self.radius, self.n,
@@ -82,15 +194,28 @@ class BilliardEnsemble:
             if bad:
                 raise ValueError(f"{bad} systems hit a separating/degenerate collision (status != 0)")
 
-    # -- read-out ------------------------------------------------------------------------------------
+    # ================================================================================================
+    # read-out
+    # ================================================================================================
     @property
     def time(self):
-        """time of the last collision of each system"""
-        return _lib.to_host(self._time)
+        """clock of each system: time of its last collision, or the end_time of the last evolve"""
+        return _lib.to_host(self._dev["time"] if self._multi else self._time)
 
     @property
     def counts(self):
+        """collisions handled so far, per system"""
+        if self._multi:
+            return _lib.to_host(self._dev["n_ball_ball"] + self._dev["n_ball_obstacle"])
         return _lib.to_host(self._counts)
+
+    @property
+    def counts_ball_ball(self):
+        return _lib.to_host(self._dev["n_ball_ball"]) if self._multi else np.zeros(self.n, dtype=np.int64)
+
+    @property
+    def counts_ball_obstacle(self):
+        return _lib.to_host(self._dev["n_ball_obstacle"]) if self._multi else self.counts
 
     @property
     def hits(self):
@@ -98,22 +223,66 @@ class BilliardEnsemble:
 
     @property
     def balls_initial_position(self):
+        if self._multi:
+            import torch
+            return _lib.to_host(torch.stack([self._dev["p0x"], self._dev["p0y"]], dim=-1))
         return _lib.to_host(self._state[0:2].T.contiguous())  # transposed on the device, one copy of what is asked for
 
     @property
+    def balls_initial_time(self):
+        return _lib.to_host(self._dev["t0"]) if self._multi else _lib.to_host(self._state[4])
+
+    @property
     def balls_velocity(self):
+        if self._multi:
+            import torch
+            return _lib.to_host(torch.stack([self._dev["vx"], self._dev["vy"]], dim=-1))
         return _lib.to_host(self._state[2:4].T.contiguous())
+
+    @property
+    def balls_position(self):
+        """positions at each system's own clock (multi-ball ensembles: what ``Billiard.balls_position`` shows)"""
+        if not self._multi:
+            s = _lib.to_host(self._state)
+            t = _lib.to_host(self._time)
+            dt = t - s[4]
+            return np.stack([s[0] + s[2] * dt, s[1] + s[3] * dt], axis=1)
+        return self._positions(0.0, 1)
+
+    def _positions(self, time, at_system_time):
+        import torch
+        h = self._handle
+        out = torch.empty((self.n, self.balls_per_system, 2), dtype=torch.float64, device=h.torch_device)
+        m = self._multi_struct()
+        h.check(h.lib.bl_multi_positions(h.h, ctypes.byref(m), float(time), int(at_system_time), _lib.ptr(out),
+                                         h.stream()))
+        return _lib.to_host(out)
+
+    @property
+    def toi_tables(self):
+        """(S, n, n) absolute impact times of every system (multi-ball ensembles), both triangles, diagonal inf"""
+        if not self._multi:
+            raise TypeError("one-ball systems have no ball-ball table")
+        if self._fresh:
+            self._run_multi(0, INF, True)
+        return _lib.to_host(self._dev["toi"])
 
     def positions_at(self, time):
         """ball positions at a common ``time`` (p0 + v*(time - t0), valid until each system's next collision)"""
+        if self._multi:
+            return self._positions(time, 0)
         s = _lib.to_host(self._state)
         dt = float(time) - s[4]
         return np.stack([s[0] + s[2] * dt, s[1] + s[3] * dt], axis=1)
 
     def stats(self):
-        """[total collisions, hits per obstacle...] summed over this process's systems (device reduction)."""
+        """Summed over this process's systems (device reduction): one-ball ensembles [total collisions, hits per
+        obstacle...]; multi-ball ensembles [total collisions, ball-ball, ball-obstacle]."""
         import torch
         h = self._handle
+        if self._multi:
+            bb, bo = self._dev["n_ball_ball"].sum(), self._dev["n_ball_obstacle"].sum()
+            return torch.stack([bb + bo, bb, bo])
         out = torch.zeros(1 + len(self.obstacles), dtype=torch.int64, device=h.torch_device)
         h.check(h.lib.bl_ensemble_stats(h.h, _lib.ptr(self._counts), _lib.ptr(self._hits), len(self.obstacles), self.n,
                                         _lib.ptr(out), h.stream()))

@@ -1,9 +1,13 @@
 """Static obstacles -- device-backed mirror of the reference's ``billiards.obstacles``.
 
-``Obstacle`` keeps the reference's two-method interface (obstacles.py:21-59); ``Disk`` (:62-76) and
-``InfiniteWall`` (:79-144) are the two kinds the CUDA event loop knows.  Their ``detect_collision`` /
-``resolve_collision`` methods run the same device functions the event kernel inlines (``bl_obstacle_detect`` /
-``bl_obstacle_resolve``), one problem per call.
+``Obstacle`` keeps the reference's two-method interface (obstacles.py:21-59); ``Disk`` (:62-76),
+``InfiniteWall`` (:79-144) and ``LineSegment`` (:147-198) are the three kinds the CUDA event loop knows.  Their
+``detect_collision`` / ``resolve_collision`` methods run the same device functions the event kernel inlines
+(``bl_obstacle_detect`` / ``bl_obstacle_resolve``), one problem per call.
+
+Not supported ("Known differences"): user-defined ``Obstacle`` subclasses -- there is no host-side
+collision loop to run their Python methods in, ``Billiard()`` raises ``NotImplementedError`` for them -- and edits of
+an obstacle's attributes after the ``Billiard`` was built (the device record is taken once, at construction).
 """
 
 from math import sqrt
@@ -30,7 +34,8 @@ class Obstacle:
 
     def _device_record(self):
         raise NotImplementedError(
-            f"{type(self).__name__} has no CUDA implementation: the B200 event loop supports Disk and InfiniteWall")
+            f"{type(self).__name__} has no CUDA implementation: the B200 event loop supports Disk, InfiniteWall and "
+            "LineSegment (there is no host-side loop that could call a Python detect_collision per event)")
 
     # -- shared device calls -------------------------------------------------------------------------
     def _detect_on_device(self, pos, vel, radius, rsum2):

@@ -446,6 +446,10 @@ class Billiard:
     # the event loop
     # ------------------------------------------------------------------------------------------------
     def _run(self, end_time, max_events=-1, first_kind=_lib.BL_ANY, log=None):
+        if end_time != end_time:
+            # the reference handles nothing for NaN (`t <= nan` is False) and then fails its own assert
+            # (simulation.py:419, :435); on the device a NaN limit would mean "never stop"
+            raise ValueError("end_time must not be NaN")
         self._flush()
         self._sync_masses()
         h = self._h()

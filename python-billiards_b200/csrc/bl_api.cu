@@ -39,11 +39,21 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
     *out = nullptr;
     bl_handle *h = new bl_handle();
     memset(h, 0, sizeof(*h));
+    {
+        pthread_mutexattr_t at;
+        pthread_mutexattr_init(&at);
+        pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+        pthread_mutex_init(&h->mutex, &at);
+        pthread_mutexattr_destroy(&at);
+    }
     h->device = device;
     h->dot_fma = dot_fma ? 1 : 0;
     *out = h;  // returned even on failure so that the caller can read the error text, then bl_destroy
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaSetDevice");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaGetDeviceCount");
+    if (device < 0 || device >= n_dev) return bl_set_error(h, BL_EINVAL, "no CUDA device %d (%d visible)", device, n_dev);
+    bl_entry_guard g(h);  // allocations below land on `device`; the caller's current device is restored on return
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaGetDeviceProperties");
@@ -83,6 +93,8 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
 
 int bl_destroy(bl_handle *h) {
     if (!h) return BL_OK;
+    {
+    bl_entry_guard g(h);
     if (h->d_result) cudaFree(h->d_result);
     if (h->d_bar) cudaFree(h->d_bar);
     if (h->d_post) cudaFree(h->d_post);
@@ -91,6 +103,8 @@ int bl_destroy(bl_handle *h) {
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    }
+    pthread_mutex_destroy(&h->mutex);
     delete h;
     return BL_OK;
 }
@@ -105,6 +119,7 @@ static int check_system(bl_handle *h, const bl_system *s) {
 }
 
 int bl_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int k, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     if (!d_idx && k > 0) return bl_set_error(h, BL_EINVAL, "bl_recompute: no index list");
@@ -112,6 +127,7 @@ int bl_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d
 }
 
 int bl_recompute_range(bl_handle *h, const bl_system *s, double time, int first, int k, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     if (k > 0 && (first < 0 || first + k > s->n))
@@ -121,6 +137,7 @@ int bl_recompute_range(bl_handle *h, const bl_system *s, double time, int first,
 
 int bl_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
                    void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_apply_edits(h, s, time, d_pos, d_vel, as_stream(stream));
@@ -140,18 +157,21 @@ int bl_host_pow2_table(const double *r, int K, double *out, const double *R, int
 }
 
 int bl_rebuild_cover(bl_handle *h, const bl_system *s, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_rebuild_cover(h, s, as_stream(stream));
 }
 
 int bl_symmetrize(bl_handle *h, const bl_system *s, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_symmetrize(h, s, as_stream(stream));
 }
 
 int bl_row_minima(bl_handle *h, const bl_system *s, double *d_balls_toi, int64_t *d_balls_idx, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_row_minima(h, s, d_balls_toi, d_balls_idx, as_stream(stream));
@@ -159,9 +179,13 @@ int bl_row_minima(bl_handle *h, const bl_system *s, double *d_balls_toi, int64_t
 
 static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                       int first_kind, const bl_log *log, int query_only, bl_result *out, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     if (!out) return BL_EINVAL;
+    // the reference processes nothing for a NaN end_time (`t <= nan` is False, simulation.py:419) and then trips its
+    // assert (:435); here a NaN would read as "no limit" and a closed table would never let the kernel return
+    if (end_time != end_time || time != time) return bl_set_error(h, BL_EINVAL, "time / end_time is NaN");
     cudaStream_t st = as_stream(stream);
     if (s->n == 0) {  // an empty table only has a clock (tests/test_simulation.py:16-27 of the reference)
         memset(out, 0, sizeof(*out));
@@ -197,6 +221,7 @@ int bl_next(bl_handle *h, const bl_system *s, double time, bl_result *out, void 
 }
 
 int bl_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, void *stream) {
+    bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
     return bl_launch_positions(h, s, time, d_pos, as_stream(stream));
@@ -204,35 +229,41 @@ int bl_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, v
 
 int bl_toi_ball_ball(bl_handle *h, const double *d_in, const double *d_rsum2, double t_eps, double *d_out, int64_t m,
                      void *stream) {
+    bl_entry_guard g(h);
     if (!h) return BL_EINVAL;
     return bl_launch_toi_batch(h, d_in, d_rsum2, t_eps, d_out, m, as_stream(stream));
 }
 
 int bl_elastic_collision(bl_handle *h, const double *d_in, double *d_out, int32_t *d_status, int64_t m, void *stream) {
+    bl_entry_guard g(h);
     if (!h) return BL_EINVAL;
     return bl_launch_elastic_batch(h, d_in, d_out, d_status, m, as_stream(stream));
 }
 
 int bl_obstacle_detect(bl_handle *h, const bl_obstacle *obstacle, const double *d_in, const double *d_rsum2,
                        double *d_out_t, double *d_out_arg, int64_t m, void *stream) {
+    bl_entry_guard g(h);
     if (!h || !obstacle) return BL_EINVAL;
     return bl_launch_obstacle_detect(h, *obstacle, d_in, d_rsum2, d_out_t, d_out_arg, m, as_stream(stream));
 }
 
 int bl_obstacle_resolve(bl_handle *h, const bl_obstacle *obstacle, const double *d_in, const double *d_arg,
                         double *d_out, int32_t *d_status, int64_t m, void *stream) {
+    bl_entry_guard g(h);
     if (!h || !obstacle) return BL_EINVAL;
     return bl_launch_obstacle_resolve(h, *obstacle, d_in, d_arg, d_out, d_status, m, as_stream(stream));
 }
 
 int bl_toi_ball_point(bl_handle *h, const double *d_in, const double *d_r2, double t_eps, double *d_out, int64_t m,
                       void *stream) {
+    bl_entry_guard g(h);
     if (!h) return BL_EINVAL;
     return bl_launch_point_batch(h, d_in, d_r2, t_eps, d_out, m, as_stream(stream));
 }
 
 int bl_toi_and_param_ball_segment(bl_handle *h, const bl_obstacle *segment, const double *d_in, double t_eps,
                                   double *d_out_t, double *d_out_u, int32_t *d_out_code, int64_t m, void *stream) {
+    bl_entry_guard g(h);
     if (!h || !segment) return BL_EINVAL;
     return bl_launch_segment_param(h, *segment, d_in, t_eps, d_out_t, d_out_u, d_out_code, m, as_stream(stream));
 }
@@ -240,6 +271,7 @@ int bl_toi_and_param_ball_segment(bl_handle *h, const bl_obstacle *segment, cons
 int bl_ensemble_run(bl_handle *h, const bl_obstacle *obstacles_host, int n_obstacles, const double *rsum2_obs_host,
                     double radius, int64_t n_sys, double *d_state, double *d_time, int64_t n_collisions,
                     double end_time, int64_t *d_counts, int32_t *d_hits, int32_t *d_status, void *stream) {
+    bl_entry_guard g(h);
     if (!h || (n_obstacles > 0 && !obstacles_host)) return BL_EINVAL;
     cudaStream_t st = as_stream(stream);
     cudaEventRecord(h->ev0, st);
@@ -251,12 +283,44 @@ int bl_ensemble_run(bl_handle *h, const bl_obstacle *obstacles_host, int n_obsta
 
 int bl_ensemble_stats(bl_handle *h, const int64_t *d_counts, const int32_t *d_hits, int n_obstacles, int64_t n_sys,
                       int64_t *d_out, void *stream) {
+    bl_entry_guard g(h);
     if (!h) return BL_EINVAL;
     return bl_launch_ensemble_stats(h, d_counts, d_hits, n_obstacles, n_sys, d_out, as_stream(stream));
 }
 
+int bl_selftest_div2(bl_handle *h, uint64_t seed, int64_t n_pairs, int64_t *mismatches, double *first_bad,
+                     void *stream) {
+    if (!h || n_pairs < 0) return BL_EINVAL;
+    bl_entry_guard g(h);
+    long long bad = 0;
+    int rc = bl_launch_selftest_div2(h, seed, n_pairs, &bad, first_bad, as_stream(stream));
+    if (mismatches) *mismatches = bad;
+    return rc;
+}
+
+int bl_multi_run(bl_handle *h, const bl_multi *m, int build_tables, double end_time, int64_t max_events, void *stream) {
+    if (!h || !m) return BL_EINVAL;
+    bl_entry_guard g(h);
+    if (m->n < 1 || m->n > BL_SMALL_MAX_BALLS || m->n_obstacles > BL_SMALL_MAX_OBS || m->n_classes < 1)
+        return bl_set_error(h, BL_EUNSUPPORTED, "bl_multi_run: systems of 1..%d balls and at most %d obstacles (n=%d, "
+                            "obstacles=%d)", BL_SMALL_MAX_BALLS, BL_SMALL_MAX_OBS, m->n, m->n_obstacles);
+    if (end_time != end_time) return bl_set_error(h, BL_EINVAL, "end_time is NaN");
+    cudaStream_t st = as_stream(stream);
+    cudaEventRecord(h->ev0, st);
+    int rc = bl_launch_multi(h, m, build_tables, end_time, max_events, st);
+    cudaEventRecord(h->ev1, st);
+    return rc;
+}
+
+int bl_multi_positions(bl_handle *h, const bl_multi *m, double time, int at_system_time, double *d_pos, void *stream) {
+    if (!h || !m || !d_pos) return BL_EINVAL;
+    bl_entry_guard g(h);
+    return bl_launch_multi_positions(h, m, time, at_system_time, d_pos, as_stream(stream));
+}
+
 int bl_last_kernel_ms(const bl_handle *h, float *ms) {
     if (!h || !ms) return BL_EINVAL;
+    bl_entry_guard g(h);
     bl_handle *hh = const_cast<bl_handle *>(h);
     if (cudaEventQuery(hh->ev1) == cudaSuccess) cudaEventElapsedTime(&hh->last_ms, hh->ev0, hh->ev1);
     *ms = hh->last_ms;
@@ -280,6 +344,12 @@ int bl_set_cta_shape_limit(bl_handle *h, int max_balls) {
 int bl_set_small_kernel(bl_handle *h, int enable) {
     if (!h) return BL_EINVAL;
     h->small_kernel_off = enable ? 0 : 1;
+    return BL_OK;
+}
+
+int bl_set_ensemble_generic(bl_handle *h, int enable) {
+    if (!h) return BL_EINVAL;
+    h->ensemble_generic = enable ? 1 : 0;
     return BL_OK;
 }
 

@@ -1,13 +1,26 @@
-// bl_evolve_small.cu -- the event loop for systems of at most 32 balls (Galperin's two balls, the pool table, Newton's
-// cradle: the reference's own examples) as ONE WARP.
+// bl_evolve_small.cu -- the event loop for systems of at most 32 balls, ONE GROUP OF LANES PER SYSTEM.
 //
-// Such systems are strictly serial -- consecutive collisions share balls, a batch would hold one collision -- so the
-// grid-wide round machinery of bl_evolve.cu buys nothing and costs a few thousand cycles per collision.  Here lane i
-// owns ball i (state of record in registers), the whole time-of-impact table sits in shared memory (both triangles
-// current), and one collision is: row minima -> warp argmin -> every lane resolves the collision redundantly from
-// shuffled states -> every other lane re-solves its two pairs -> the colliding lanes refresh their obstacle entry.
-// No barrier but __syncwarp.  Same arithmetic, same keys, same stop rules as the big kernel; same reference lines:
-// simulation.py:354-438, :440-502, :504-554, :556-560, :562-636.
+// Galperin's two balls, the pool table, Newton's cradle (the reference's own examples) are strictly serial --
+// consecutive collisions share balls, a batch would hold one collision -- so the grid-wide round machinery of
+// bl_evolve.cu buys nothing there.  Here a system of n balls is served by W = 2, 4, 8, 16 or 32 lanes of one warp
+// (the smallest power of two >= n): lane i owns ball i (state of record in registers), the system's whole
+// time-of-impact table sits in shared memory (both triangles current), and one collision is: row minima -> group
+// argmin (xor butterfly over the W lanes) -> every lane resolves the collision redundantly from shuffled states ->
+// every other lane re-solves its pair(s) with the colliding ball(s) -> the colliding lanes refresh their obstacle
+// entry.  No barrier but __syncwarp on the group's lanes.
+//
+// The same kernel serves
+//   * a single Billiard (bl_evolve / bl_next on a bl_system with n <= 32): SINGLE = true, one group, with the
+//     event log, the forced first kind of bounce_ball_ball / bounce_ball_obstacle and the next-collision queries;
+//   * ENSEMBLES of independent multi-ball billiards (bl_multi_run): SINGLE = false, 32 / W systems per warp, four
+//     warps per CTA, systems sharded over CTAs (and over GPUs by the caller) -- north_star's "one system per warp or
+//     CTA, ball state staged in shared memory".  Every system is exactly "a Billiard with these balls": same
+//     arithmetic, same keys, same stop rules, so an ensemble of one reproduces the single path bit for bit.
+//
+// Reference lines restated: simulation.py:354-438 (evolve), :440-502 (bounce_ball_ball), :504-554
+// (bounce_ball_obstacle), :556-560 (_move), :562-636 (resolve), :176-209 (add_ball's row, for table builds).
+#include <cstring>
+
 #include "bl_arith.cuh"
 #include "bl_internal.h"
 
@@ -15,96 +28,156 @@ namespace {
 
 enum { KIND_BOTH = 0, KIND_BB = 1, KIND_BO = 2 };
 
+#define BL_SMALL_WARPS 4  // warps per CTA in ensemble launches
+
 struct SmallParams {
-    bl_system s;
-    double time, end_time;
+    long long n_sys;
+    int n, K, n_obs;
+    int toi_pitch;             // row pitch of one system's table in doubles
+    long long toi_sys_stride;  // doubles between the tables of consecutive systems
+    double *p0x, *p0y, *vx, *vy, *t0;  // ball i of system s at [s*n + i]
+    const double *radius, *mass;       // [n]
+    const int32_t *rclass;             // [n]
+    const double *rsum2, *rsum2_obs;
+    const bl_obstacle *obstacles;
+    double *toi;
+    double *obs_t, *obs_arg;
+    int32_t *obs_idx;
+    double end_time;
     long long max_events;
-    int first_kind;
-    int query_only;
+    // single system only
+    double time;
+    int first_kind, query_only;
     bl_log log;
     bl_result *result;
+    double *cover_t;
+    uint64_t *cover_code;
+    int64_t *seq_counter;
+    // ensembles only
+    int build_tables;          // solve every pair at the system's current time first (what add_ball does row by row)
+    double *sys_time;
+    int64_t *n_bb, *n_bo;
+    int32_t *status;
 };
 
-__device__ __forceinline__ int warp_argmin_s(uint64_t ts, uint64_t code) {
-    const unsigned FULL = 0xffffffffu;
-    unsigned x = (unsigned)(ts >> 32);
-    unsigned m = __reduce_min_sync(FULL, x);
-    bool c = x == m;
-    x = c ? (unsigned)ts : 0xffffffffu;
-    m = __reduce_min_sync(FULL, x);
-    c = c && x == m;
-    x = c ? (unsigned)(code >> 32) : 0xffffffffu;
-    m = __reduce_min_sync(FULL, x);
-    c = c && x == m;
-    x = c ? (unsigned)code : 0xffffffffu;
-    m = __reduce_min_sync(FULL, x);
-    c = c && x == m;
-    return __ffs(__ballot_sync(FULL, c)) - 1;
+// lexicographic (time, code): numpy's first-index argmin (FP compare, so -0.0 == 0.0 like there) with the pair /
+// obstacle codes of bl_arith.cuh breaking ties
+__device__ __forceinline__ bool key_less(double ta, uint64_t ca, double tb, uint64_t cb) {
+    return ta < tb || (ta == tb && ca < cb);
 }
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ uint64_t shfl_u(uint64_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template <bool FMA>
-__global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_constant__ SmallParams P) {
-    __shared__ double T[32][33];
-    __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
-    const bl_system &S = P.s;
-    const int n = S.n, K = S.n_classes, n_obs = S.n_obstacles;
-    const int lane = threadIdx.x;
-    const bool own = lane < n;
-    for (int q = lane; q < n_obs; q += 32) s_obs[q] = S.obstacles[q];
-    double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0, mass = 0, radius = 0, oarg = 0;
-    uint64_t ots = bl_sortable(BL_INF);
-    int rc = 0, oidx = -1;
-    if (own) {
-        p0x = S.p0x[lane]; p0y = S.p0y[lane]; vx = S.vx[lane]; vy = S.vy[lane]; t0 = S.t0[lane];
-        mass = S.mass[lane]; radius = S.radius[lane]; rc = S.rclass[lane];
-        ots = bl_sortable(S.obs_t[lane]); oarg = S.obs_arg[lane]; oidx = S.obs_idx[lane];
-        for (int j = 0; j < n; j++) T[lane][j] = S.toi[(size_t)lane * S.pitch + j];
+template <int W>
+__device__ __forceinline__ void group_min(unsigned gmask, double &t, uint64_t &c) {
+#pragma unroll
+    for (int o = 1; o < W; o <<= 1) {
+        const double t2 = __shfl_xor_sync(gmask, t, o, W);
+        const uint64_t c2 = __shfl_xor_sync(gmask, c, o, W);
+        const bool take = key_less(t2, c2, t, c);
+        t = take ? t2 : t;
+        c = take ? c2 : c;
     }
-    __syncwarp();
+}
 
-    const uint64_t ts_inf = bl_sortable(BL_INF);
-    uint64_t end_excl = bl_sortable(P.end_time);
-    end_excl = end_excl >= ts_inf ? ts_inf : end_excl + 1;
-    const bool want_log = P.log.cap > 0;
+template <bool FMA, int W, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
+    bl_evolve_small_kernel(const __grid_constant__ SmallParams P) {
+    // one table row per lane: row (warp, lane) = T[ball li of that lane's system][0..W), padded to W + 1 (odd pitch:
+    // the 32 lanes of a warp hit distinct banks whatever W is)
+    extern __shared__ double smem[];
+    __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
+    constexpr int RP = W + 1;
+    const int n = P.n, K = P.K, n_obs = P.n_obs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int li = lane & (W - 1);                      // my ball
+    const int gbase = lane & ~(W - 1);                  // first lane of my group
+    const unsigned gmask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << gbase);
+    double *const Tw = smem + (size_t)warp * 32 * RP;   // this warp's rows
+    double *const Trow = Tw + (size_t)lane * RP;        // my row
+    double *const Tg = Tw + (size_t)gbase * RP;         // row 0 of my group: row of ball a = Tg + a * RP
+    for (int q = threadIdx.x; q < n_obs; q += blockDim.x) s_obs[q] = P.obstacles[q];
+    __syncthreads();
+    const long long sys = SINGLE ? (lane / W) : ((long long)blockIdx.x * BL_SMALL_WARPS + warp) * (32 / W) + (lane / W);
+    if (sys >= P.n_sys) return;  // whole groups leave together: every later sync names the group's lanes only
+    const bool own = li < n;
+    const long long sb = sys * n;  // first ball of my system
+
+    double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0, mass = 0, radius = 0, oarg = 0, ot = BL_INF;
+    int rc = 0, oidx = -1;
+    double now = SINGLE ? P.time : P.sys_time[sys];
+    if (own) {
+        p0x = P.p0x[sb + li]; p0y = P.p0y[sb + li]; vx = P.vx[sb + li]; vy = P.vy[sb + li]; t0 = P.t0[sb + li];
+        mass = P.mass[li]; radius = P.radius[li]; rc = P.rclass[li];
+    }
+    const double *const rs_row = P.rsum2 + (size_t)rc * K;  // (r_me + r_x)**2 by the class of x
+    const double rs_one = P.rsum2[0];
+    if (!SINGLE && P.build_tables) {
+        // add_ball, row by row at the current time (simulation.py:176-209): every pair solved from the positions of
+        // `now`; the solve is bit-symmetric in the two balls, so lane i fills its own row
+        const double px = bl_advance(p0x, vx, now, t0), py = bl_advance(p0y, vy, now, t0);
+        for (int j = 0; j < W; j++) {
+            const double jx = __shfl_sync(gmask, px, j, W), jy = __shfl_sync(gmask, py, j, W);
+            const double jvx = __shfl_sync(gmask, vx, j, W), jvy = __shfl_sync(gmask, vy, j, W);
+            const int jrc = __shfl_sync(gmask, rc, j, W);
+            double v = BL_INF;
+            if (own && j < n && j != li)
+                v = bl_add(now, bl_toi_ball_ball<FMA>(px, py, vx, vy, jx, jy, jvx, jvy, K == 1 ? rs_one : rs_row[jrc]));
+            Trow[j] = v;
+        }
+        if (own) {
+            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc, px, py, vx, vy, radius, now, ot, oidx, oarg);
+        }
+    } else {
+        if (own) {
+            ot = P.obs_t[sb + li]; oarg = P.obs_arg[sb + li]; oidx = P.obs_idx[sb + li];
+            const double *src = P.toi + sys * P.toi_sys_stride + (size_t)li * P.toi_pitch;
+            for (int j = 0; j < n; j++) Trow[j] = src[j];
+            Trow[li] = BL_INF;
+        } else {
+            for (int j = 0; j < n; j++) Trow[j] = BL_INF;
+        }
+    }
+    __syncwarp(gmask);
+
+    const bool want_log = SINGLE && P.log.cap > 0;
     bl_result *const res = P.result;
     long long done = 0, n_bb = 0;
-    double now = P.time;
-    int kindmask = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
-    int final_stage = P.query_only ? 1 : 0;
-    if (final_stage == 1) kindmask = KIND_BB;
+    int kindmask = KIND_BOTH, final_stage = 0;
+    if (SINGLE) {
+        kindmask = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
+        if (P.query_only) { final_stage = 1; kindmask = KIND_BB; }
+    }
+    int end_stop = BL_STOP_TIME, end_status = BL_OK;
 
     for (;;) {
         // ---- my key: minimum of my table row (first index on ties), or my next obstacle ----
-        uint64_t kts = ~0ull, kcode = BL_CODE_END;
+        double kt = BL_INF;
+        uint64_t kc = BL_CODE_END;
         if (own) {
             if (kindmask != KIND_BO) {
-                kts = ts_inf; kcode = BL_CODE_NONE;
+                int bj = -1;
                 for (int j = 0; j < n; j++) {
-                    const double v = T[lane][j];
-                    if (j != lane && v < BL_INF) {
-                        const uint64_t s2 = bl_sortable(v), c2 = bl_pair_code(lane, j);
-                        if (bl_key_less(s2, c2, kts, kcode)) { kts = s2; kcode = c2; }
-                    }
+                    const double v = Trow[j];
+                    const bool lt = v < kt;
+                    kt = lt ? v : kt;
+                    bj = lt ? j : bj;
                 }
+                kc = bj >= 0 ? bl_pair_code(li, bj) : BL_CODE_NONE;
             }
             if (kindmask != KIND_BB) {
-                const uint64_t oc = BL_CODE_OBS | (uint64_t)lane;
-                if (kindmask == KIND_BO || bl_key_less(ots, oc, kts, kcode)) { kts = ots; kcode = oc; }
+                // a ball-ball collision wins a tie (simulation.py:421), a NaN obstacle time never wins
+                if (kindmask == KIND_BO || ot < kt) { kt = ot; kc = BL_CODE_OBS | (uint64_t)li; }
             }
         }
-        const int w = warp_argmin_s(kts, kcode);
-        const uint64_t ts = shfl_u(kts, w), cd = shfl_u(kcode, w);
-        const double t = bl_unsortable(ts);
+        group_min<W>(gmask, kt, kc);
+        const double t = kt;
+        const uint64_t cd = kc;
 
-        // ---- stop rules (same order as the analysis of bl_evolve.cu) ----
+        // ---- stop rules ----
         int stop_kind = -1, st_status = BL_OK;
-        const bool max_reached = P.max_events >= 0 && done >= P.max_events;
-        if (final_stage == 0 && max_reached) stop_kind = BL_STOP_EVENTS;
-        else if (final_stage != 0) stop_kind = BL_STOP_TIME;
-        else if (ts == BL_TS_NAN) { stop_kind = BL_STOP_ERROR; st_status = BL_ENAN; }
-        else if (ts >= end_excl) stop_kind = BL_STOP_TIME;
+        if (SINGLE && final_stage != 0) stop_kind = BL_STOP_TIME;
+        else if (P.max_events >= 0 && done >= P.max_events) stop_kind = BL_STOP_EVENTS;
+        else if (t != t) { stop_kind = BL_STOP_ERROR; st_status = BL_ENAN; }
+        else if (!(t <= P.end_time) || !(t < BL_INF) || cd == BL_CODE_NONE || cd == BL_CODE_END) stop_kind = BL_STOP_TIME;
         else if (want_log && done >= P.log.cap) stop_kind = BL_STOP_LOG;
 
         int a = -1, b = -1;
@@ -116,15 +189,17 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
         double a_vx = 0, a_vy = 0, b_vx = 0, b_vy = 0, qarg = 0;
         int oi = -1, rca = 0, rcb = 0;
         if (stop_kind < 0) {
-            // ---- resolve, redundantly in every lane (states come by shuffle) ----
-            const int sa = a, sb = b >= 0 ? b : a;
-            const double a0x = shfl_d(p0x, sa), a0y = shfl_d(p0y, sa), a_t0 = shfl_d(t0, sa), am = shfl_d(mass, sa);
-            a_vx = shfl_d(vx, sa); a_vy = shfl_d(vy, sa);
-            const double b0x = shfl_d(p0x, sb), b0y = shfl_d(p0y, sb), b_t0 = shfl_d(t0, sb), bm = shfl_d(mass, sb);
-            b_vx = shfl_d(vx, sb); b_vy = shfl_d(vy, sb);
-            qarg = shfl_d(oarg, sa);
-            oi = __shfl_sync(0xffffffffu, oidx, sa);
-            rca = __shfl_sync(0xffffffffu, rc, sa); rcb = __shfl_sync(0xffffffffu, rc, sb);
+            // ---- resolve, redundantly in every lane of the group (states come by shuffle) ----
+            const int sa = a, sb2 = b >= 0 ? b : a;
+            const double a0x = __shfl_sync(gmask, p0x, sa, W), a0y = __shfl_sync(gmask, p0y, sa, W);
+            const double a_t0 = __shfl_sync(gmask, t0, sa, W), am = __shfl_sync(gmask, mass, sa, W);
+            a_vx = __shfl_sync(gmask, vx, sa, W); a_vy = __shfl_sync(gmask, vy, sa, W);
+            const double b0x = __shfl_sync(gmask, p0x, sb2, W), b0y = __shfl_sync(gmask, p0y, sb2, W);
+            const double b_t0 = __shfl_sync(gmask, t0, sb2, W), bm = __shfl_sync(gmask, mass, sb2, W);
+            b_vx = __shfl_sync(gmask, vx, sb2, W); b_vy = __shfl_sync(gmask, vy, sb2, W);
+            qarg = __shfl_sync(gmask, oarg, sa, W);
+            oi = __shfl_sync(gmask, oidx, sa, W);
+            rca = __shfl_sync(gmask, rc, sa, W); rcb = __shfl_sync(gmask, rc, sb2, W);
             ax = bl_advance(a0x, a_vx, t, a_t0); ay = bl_advance(a0y, a_vy, t, a_t0);
             int st;
             if (b < 0) {
@@ -139,18 +214,14 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
             }
             if (st != BL_OK) {
                 // the reference has moved to t and raised; the collision is not applied
-                if (lane == 0) {
-                    res->err_i = a; res->err_j = b; res->time = t; res->stop = BL_STOP_ERROR; res->status = st;
-                    res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb; res->n_logged = want_log ? done : 0;
-                }
+                stop_kind = BL_STOP_ERROR; st_status = st;
                 now = t;
-                final_stage = 1; kindmask = KIND_BB;
-                continue;
             }
         }
         if (stop_kind >= 0) {
+            if (!SINGLE) { end_stop = stop_kind; end_status = st_status; break; }
             if (final_stage == 0) {
-                if (lane == 0) {
+                if (li == 0) {
                     double tnow = now;
                     res->err_i = -1; res->err_j = -1;
                     if (st_status != BL_OK) { res->err_i = a; res->err_j = b; tnow = t; }
@@ -163,7 +234,7 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
                 continue;
             }
             if (final_stage == 1) {
-                if (lane == 0) {
+                if (li == 0) {
                     if (P.query_only) { res->time = P.time; res->err_i = -1; res->err_j = -1; }
                     const bool some = cd != BL_CODE_NONE && cd != BL_CODE_END && t < BL_INF;
                     res->bb_t = some ? t : BL_INF; res->bb_i = some ? bl_code_lo(cd) : -1; res->bb_j = some ? bl_code_hi(cd) : 0;
@@ -174,9 +245,9 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
             // numpy argmin over _obstacles_toi: first ball attaining the minimum, even when it is +inf
             const bool some = cd != BL_CODE_END;
             const int ball = some ? (int)(cd & 0x7fffffffull) : 0;
-            const int q_oi = __shfl_sync(0xffffffffu, oidx, ball);
-            const double q_arg = shfl_d(oarg, ball);
-            if (lane == 0) {
+            const int q_oi = __shfl_sync(gmask, oidx, ball, W);
+            const double q_arg = __shfl_sync(gmask, oarg, ball, W);
+            if (li == 0) {
                 res->bo_t = some ? t : BL_INF; res->bo_ball = some ? ball : -1;
                 res->bo_obs = some ? q_oi : -1; res->bo_arg = some ? q_arg : 0.0;
             }
@@ -184,7 +255,7 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
         }
 
         // ---- log, simulation.py:590-594 / :626-631 payloads ----
-        if (want_log && lane == 0) {
+        if (want_log && li == 0) {
             const long long e = done;
             P.log.t[e] = t; P.log.i[e] = a; P.log.j[e] = b >= 0 ? (long long)b : -1 - (long long)oi;
             if (P.log.payload) {
@@ -194,30 +265,26 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
                 else { o[6] = qarg; o[7] = 0; o[8] = 0; o[9] = 0; o[10] = 0; o[11] = 0; }
             }
         }
-        // ---- every other ball re-solves its pair with the colliding ball(s); simulation.py:461-471, :522-526 ----
-        if (own && lane != a && lane != b) {
+        if (own && li != a && li != b) {
+            // ---- every other ball re-solves its pair with the colliding ball(s); simulation.py:461-471, :522-526 ----
             const double px = bl_advance(p0x, vx, t, t0), py = bl_advance(p0y, vy, t, t0);
-            const double rsa = S.rsum2[(size_t)rca * K + rc];
+            const double rsa = K == 1 ? rs_one : rs_row[rca];
             const double va = bl_add(t, bl_toi_ball_ball<FMA>(ax, ay, avx, avy, px, py, vx, vy, rsa));
-            T[lane][a] = va; T[a][lane] = va;
+            Trow[a] = va; Tg[a * RP + li] = va;
             if (b >= 0) {
-                const double rsb = S.rsum2[(size_t)rcb * K + rc];
+                const double rsb = K == 1 ? rs_one : rs_row[rcb];
                 const double vb = bl_add(t, bl_toi_ball_ball<FMA>(bx, by, bvx, bvy, px, py, vx, vy, rsb));
-                T[lane][b] = vb; T[b][lane] = vb;
+                Trow[b] = vb; Tg[b * RP + li] = vb;
             }
-        }
-        // ---- the colliding balls: new state of record, pair entry = inf (:458), next obstacle (:490-495, :545-547) ----
-        if (lane == a || lane == b) {
-            if (lane == a) { p0x = ax; p0y = ay; vx = avx; vy = avy; }
+        } else if (own) {
+            // ---- the colliding balls: new state of record, pair entry = inf (:458), next obstacle (:490-495, :545-547) ----
+            if (li == a) { p0x = ax; p0y = ay; vx = avx; vy = avy; }
             else { p0x = bx; p0y = by; vx = bvx; vy = bvy; }
             t0 = t;
-            if (b >= 0) T[lane][lane == a ? b : a] = BL_INF;
-            double ot, na;
-            int ni;
-            bl_next_obstacle<FMA>(s_obs, n_obs, S.rsum2_obs, K, rc, p0x, p0y, vx, vy, radius, t, ot, ni, na);
-            ots = bl_sortable(ot); oarg = na; oidx = ni;
+            if (b >= 0) Trow[li == a ? b : a] = BL_INF;
+            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc, p0x, p0y, vx, vy, radius, t, ot, oidx, oarg);
         }
-        __syncwarp();
+        __syncwarp(gmask);
         done++;
         n_bb += b >= 0 ? 1 : 0;
         now = t;
@@ -226,25 +293,68 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
 
     // ---- write the state, the table and the caches back ----
     if (own) {
-        S.p0x[lane] = p0x; S.p0y[lane] = p0y; S.vx[lane] = vx; S.vy[lane] = vy; S.t0[lane] = t0;
-        S.obs_t[lane] = bl_unsortable(ots); S.obs_arg[lane] = oarg; S.obs_idx[lane] = oidx;
-        uint64_t mts = ts_inf, mcode = BL_CODE_NONE;
+        P.p0x[sb + li] = p0x; P.p0y[sb + li] = p0y; P.vx[sb + li] = vx; P.vy[sb + li] = vy; P.t0[sb + li] = t0;
+        P.obs_t[sb + li] = ot; P.obs_arg[sb + li] = oarg; P.obs_idx[sb + li] = oidx;
+        double *dst = P.toi + sys * P.toi_sys_stride + (size_t)li * P.toi_pitch;
+        double mt = BL_INF;
+        int mj = -1;
         for (int j = 0; j < n; j++) {
-            const double v = T[lane][j];
-            S.toi[(size_t)lane * S.pitch + j] = v;
-            if (j != lane && v < BL_INF) {
-                const uint64_t s2 = bl_sortable(v), c2 = bl_pair_code(lane, j);
-                if (bl_key_less(s2, c2, mts, mcode)) { mts = s2; mcode = c2; }
-            }
+            const double v = Trow[j];
+            dst[j] = v;
+            const bool lt = v < mt;
+            mt = lt ? v : mt;
+            mj = lt ? j : mj;
         }
-        S.cover_t[lane] = bl_unsortable(mts); S.cover_code[lane] = mcode;
+        if (SINGLE) { P.cover_t[li] = mt; P.cover_code[li] = mj >= 0 ? bl_pair_code(li, mj) : BL_CODE_NONE; }
     }
-    if (lane == 0) {
-        for (int q = 0; q < 16; q++) res->prof[q] = 0;
-        res->prof[5] = done;
-        res->window = 0.0;
-        *S.seq_counter += done;
+    if (li == 0) {
+        if (SINGLE) {
+            for (int q = 0; q < 16; q++) res->prof[q] = 0;
+            res->prof[5] = done;
+            res->window = 0.0;
+            *P.seq_counter += done;
+        } else {
+            // _move(end_time) when the limit was a time (simulation.py:436); otherwise the clock of the last collision
+            P.sys_time[sys] = (end_stop == BL_STOP_TIME && P.end_time < BL_INF) ? P.end_time : now;
+            P.n_bb[sys] += n_bb; P.n_bo[sys] += done - n_bb;
+            P.status[sys] = end_status;
+        }
     }
+}
+
+// positions of every ball of every system at `time` (or at its own system's clock): _move as a projection
+__global__ void __launch_bounds__(256) bl_multi_positions_kernel(const long long total, const int n,
+                                                                  const double *__restrict__ p0x,
+                                                                  const double *__restrict__ p0y,
+                                                                  const double *__restrict__ vx,
+                                                                  const double *__restrict__ vy,
+                                                                  const double *__restrict__ t0,
+                                                                  const double *__restrict__ sys_time, const double time,
+                                                                  const int at_system_time, double *__restrict__ pos) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const double t = at_system_time ? sys_time[k / n] : time;
+        pos[2 * k] = bl_advance(p0x[k], vx[k], t, t0[k]);
+        pos[2 * k + 1] = bl_advance(p0y[k], vy[k], t, t0[k]);
+    }
+}
+
+template <bool FMA, bool SINGLE>
+cudaError_t launch_w(const SmallParams &P, int sm_count, cudaStream_t st) {
+    int W = 2;
+    while (W < P.n) W <<= 1;
+#define BL_SMALL_LAUNCH(WW)                                                                                            \
+    if (W == WW) {                                                                                                     \
+        const int warps = SINGLE ? 1 : BL_SMALL_WARPS;                                                                 \
+        const size_t smem = (size_t)warps * 32 * (WW + 1) * sizeof(double);                                            \
+        const long long per_cta = (long long)warps * (32 / WW);                                                        \
+        const unsigned grid = SINGLE ? 1u : (unsigned)((P.n_sys + per_cta - 1) / per_cta);                             \
+        bl_evolve_small_kernel<FMA, WW, SINGLE><<<grid, 32 * warps, smem, st>>>(P);                                    \
+        return cudaGetLastError();                                                                                     \
+    }
+    BL_SMALL_LAUNCH(2) BL_SMALL_LAUNCH(4) BL_SMALL_LAUNCH(8) BL_SMALL_LAUNCH(16) BL_SMALL_LAUNCH(32)
+#undef BL_SMALL_LAUNCH
+    (void)sm_count;
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -252,15 +362,52 @@ __global__ void __launch_bounds__(32, 1) bl_evolve_small_kernel(const __grid_con
 int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                            int first_kind, const bl_log *log, int query_only, cudaStream_t st) {
     SmallParams P;
-    P.s = *s;
-    P.time = time; P.end_time = end_time; P.max_events = max_events; P.first_kind = first_kind;
-    P.query_only = query_only;
-    if (log) P.log = *log; else { P.log.cap = 0; P.log.t = nullptr; P.log.i = nullptr; P.log.j = nullptr; P.log.payload = nullptr; }
+    memset(&P, 0, sizeof(P));
+    P.n_sys = 1; P.n = s->n; P.K = s->n_classes; P.n_obs = s->n_obstacles;
+    P.toi_pitch = s->pitch; P.toi_sys_stride = 0;
+    P.p0x = s->p0x; P.p0y = s->p0y; P.vx = s->vx; P.vy = s->vy; P.t0 = s->t0;
+    P.radius = s->radius; P.mass = s->mass; P.rclass = s->rclass;
+    P.rsum2 = s->rsum2; P.rsum2_obs = s->rsum2_obs; P.obstacles = s->obstacles;
+    P.toi = s->toi; P.obs_t = s->obs_t; P.obs_arg = s->obs_arg; P.obs_idx = s->obs_idx;
+    P.end_time = end_time; P.max_events = max_events;
+    P.time = time; P.first_kind = first_kind; P.query_only = query_only;
+    if (log) P.log = *log;
     P.result = h->d_result;
+    P.cover_t = s->cover_t; P.cover_code = s->cover_code; P.seq_counter = s->seq_counter;
     cudaError_t e = cudaMemsetAsync(h->d_result, 0, sizeof(bl_result), st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset result");
     h->launches++;
-    if (h->dot_fma) bl_evolve_small_kernel<true><<<1, 32, 0, st>>>(P);
-    else bl_evolve_small_kernel<false><<<1, 32, 0, st>>>(P);
-    return bl_check_cuda(h, cudaGetLastError(), "launch bl_evolve_small_kernel");
+    e = h->dot_fma ? launch_w<true, true>(P, h->sm_count, st) : launch_w<false, true>(P, h->sm_count, st);
+    return bl_check_cuda(h, e, "launch bl_evolve_small_kernel");
+}
+
+int bl_launch_multi(bl_handle *h, const bl_multi *m, int build_tables, double end_time, long long max_events,
+                    cudaStream_t st) {
+    if (m->n_sys <= 0) return BL_OK;
+    SmallParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_sys = m->n_sys; P.n = m->n; P.K = m->n_classes; P.n_obs = m->n_obstacles;
+    P.toi_pitch = m->n; P.toi_sys_stride = (long long)m->n * m->n;
+    P.p0x = m->p0x; P.p0y = m->p0y; P.vx = m->vx; P.vy = m->vy; P.t0 = m->t0;
+    P.radius = m->radius; P.mass = m->mass; P.rclass = m->rclass;
+    P.rsum2 = m->rsum2; P.rsum2_obs = m->rsum2_obs; P.obstacles = m->obstacles;
+    P.toi = m->toi; P.obs_t = m->obs_t; P.obs_arg = m->obs_arg; P.obs_idx = m->obs_idx;
+    P.end_time = end_time; P.max_events = max_events;
+    P.build_tables = build_tables;
+    P.sys_time = m->time; P.n_bb = m->n_ball_ball; P.n_bo = m->n_ball_obstacle; P.status = m->status;
+    h->launches++;
+    cudaError_t e = h->dot_fma ? launch_w<true, false>(P, h->sm_count, st) : launch_w<false, false>(P, h->sm_count, st);
+    return bl_check_cuda(h, e, "launch bl_evolve_small_kernel (ensemble)");
+}
+
+int bl_launch_multi_positions(bl_handle *h, const bl_multi *m, double time, int at_system_time, double *d_pos,
+                              cudaStream_t st) {
+    const long long total = m->n_sys * m->n;
+    if (total <= 0) return BL_OK;
+    const long long want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < 8LL * h->sm_count ? want : 8LL * h->sm_count);
+    bl_multi_positions_kernel<<<grid, 256, 0, st>>>(total, m->n, m->p0x, m->p0y, m->vx, m->vy, m->t0, m->time, time,
+                                                    at_system_time, d_pos);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_multi_positions_kernel");
 }

@@ -1,10 +1,13 @@
 // bl_internal.h -- launcher prototypes shared by the translation units of libbilliards_b200.so
 #pragma once
 #include <cuda_runtime.h>
+#include <pthread.h>
 
 #include "../../include/billiards_b200.h"
 
 struct bl_handle {
+    pthread_mutex_t mutex;    // one library call at a time per handle (the handle owns barrier counters, exchange
+                              // buffers and ONE result block: two concurrent launches would race on them)
     int device;
     int dot_fma;
     int sm_count;
@@ -49,6 +52,28 @@ struct bl_handle {
 #define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
 
+// Every extern "C" entry that touches the device starts with `bl_entry_guard g(h);`: it serialises the calls on one
+// handle and makes the handle's device current for the duration of the call (a kernel launch on a stream of a
+// non-current device fails, and cudaFuncSetAttribute would land on the wrong device), restoring the caller's device
+// on the way out.
+struct bl_entry_guard {
+    bl_handle *h;
+    int prev;
+    bool switched;
+    explicit bl_entry_guard(const bl_handle *handle) : h(const_cast<bl_handle *>(handle)), prev(-1), switched(false) {
+        if (!h) return;
+        pthread_mutex_lock(&h->mutex);
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+    }
+    ~bl_entry_guard() {
+        if (!h) return;
+        if (switched) cudaSetDevice(prev);
+        pthread_mutex_unlock(&h->mutex);
+    }
+    bl_entry_guard(const bl_entry_guard &) = delete;
+    bl_entry_guard &operator=(const bl_entry_guard &) = delete;
+};
+
 int bl_set_error(bl_handle *h, int code, const char *fmt, ...);
 int bl_check_cuda(bl_handle *h, cudaError_t e, const char *what);
 
@@ -57,6 +82,10 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st);
 int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                            int first_kind, const bl_log *log, int query_only, cudaStream_t st);
+int bl_launch_multi(bl_handle *h, const bl_multi *m, int build_tables, double end_time, long long max_events,
+                    cudaStream_t st);
+int bl_launch_multi_positions(bl_handle *h, const bl_multi *m, double time, int at_system_time, double *d_pos,
+                              cudaStream_t st);
 int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode);
 // bl_table.cu
 int bl_launch_recompute(bl_handle *h, const bl_system *s, double time, const int32_t *d_idx, int first, int k,
@@ -84,5 +113,7 @@ int bl_launch_segment_param(bl_handle *h, bl_obstacle sg, const double *d_in, do
 int bl_launch_ensemble(bl_handle *h, const bl_obstacle *obs, int n_obs, const double *rsum2_obs, double radius,
                        long long n_sys, double *d_state, double *d_time, long long n_coll, double end_time,
                        int64_t *d_counts, int32_t *d_hits, int32_t *d_status, cudaStream_t st);
+int bl_launch_selftest_div2(bl_handle *h, uint64_t seed, long long n, long long *mismatches, double *first_bad,
+                            cudaStream_t st);
 int bl_launch_ensemble_stats(bl_handle *h, const int64_t *d_counts, const int32_t *d_hits, int n_obs, long long n_sys,
                              int64_t *d_out, cudaStream_t st);
