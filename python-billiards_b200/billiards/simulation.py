@@ -473,14 +473,71 @@ class Billiard:
         h.check(rc)
         return res
 
+    #: how ``evolve`` serves callbacks.  "replay" (default): the whole interval is ONE kernel launch that writes a
+    #: device event log with the callback payloads; the log is copied back once and replayed on the host (``time`` is
+    #: set to each collision's time while its callbacks run; the arrays ``balls_position`` / ``balls_velocity`` /
+    #: ``toi_table`` read inside a callback show the END of the launch, the per-collision numbers are the callback's
+    #: arguments).  "step": one launch per collision, so the billiard's arrays are current after every collision --
+    #: for callbacks that inspect or edit the billiard itself.
+    callback_mode = "replay"
+    #: collisions logged per launch in replay mode (the launch stops when the log is full and is continued)
+    callback_log_capacity = 1 << 16
+
+    def _log_buffers(self, cap):
+        """Device event log (t, i, j, payload[12]) as ONE allocation plus a pinned host mirror, cached per Billiard."""
+        import torch
+        cur = getattr(self, "_logbuf", None)
+        if cur is None or cur[0] < cap:
+            dev = self._h().torch_device
+            d = torch.zeros(15 * cap, dtype=torch.float64, device=dev)
+            hbuf = torch.zeros(15 * cap, dtype=torch.float64, pin_memory=True)
+            cur = (cap, d, hbuf)
+            self._logbuf = cur
+        cap, d, hbuf = cur
+        log = _lib.BlLog(cap, d[0:].data_ptr(), d[cap:].data_ptr(), d[2 * cap:].data_ptr(), d[3 * cap:].data_ptr())
+        return cap, d, hbuf, log
+
+    def _read_log(self, k, cap, d, hbuf, payload=True):
+        """first k records of the device log -> numpy (t, i, j, payload) through the pinned mirror: one sync"""
+        import torch
+        if k == 0:
+            return (np.empty(0), np.empty(0, dtype=_I64), np.empty(0, dtype=_I64), np.empty((0, 12)))
+        for q in range(3):
+            hbuf[q * cap:q * cap + k].copy_(d[q * cap:q * cap + k], non_blocking=True)
+        if payload:
+            hbuf[3 * cap:3 * cap + 12 * k].copy_(d[3 * cap:3 * cap + 12 * k], non_blocking=True)
+        torch.cuda.current_stream(self._h().torch_device).synchronize()
+        hn = hbuf.numpy()
+        return (hn[0:k].copy(), hn[cap:cap + k].view(_I64).copy(), hn[2 * cap:2 * cap + k].view(_I64).copy(),
+                hn[3 * cap:3 * cap + 12 * k].reshape(k, 12).copy() if payload else None)
+
+    def _call_back(self, t, i, j, p, ball_callbacks, obstacle_callbacks):
+        """the callbacks of one logged collision, in the reference's order (simulation.py:590-594, :626-631)"""
+        if j >= 0:
+            if ball_callbacks:
+                if i in ball_callbacks:
+                    ball_callbacks[i](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), j)
+                if j in ball_callbacks:
+                    ball_callbacks[j](t, p[6:8].copy(), p[8:10].copy(), p[10:12].copy(), i)
+        else:
+            obs, args = self._obs_and_args(-1 - j, p[6])
+            if ball_callbacks and i in ball_callbacks:
+                ball_callbacks[i](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), obs)
+            if obstacle_callbacks and obs in obstacle_callbacks:
+                obstacle_callbacks[obs](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), args, i)
+
     def evolve(self, end_time, time_callback=None, ball_callbacks=None, obstacle_callbacks=None):
         """Advance the simulation to ``end_time``; returns ``(ball-ball, ball-obstacle)`` collision counts
         (simulation.py:354-438).
 
-        Without callbacks the whole interval is ONE kernel launch.  With callbacks the kernel is stepped one
-        collision at a time so that every callback sees the billiard exactly as the reference would show it:
-        ``time_callback(t)``; ``ball_callbacks[i](t, pos, vel_before, vel_after, other ball or obstacle)``;
-        ``obstacle_callbacks[obs](t, pos, vel_before, vel_after, args, ball)``.
+        Without callbacks the whole interval is ONE kernel launch.  With callbacks it still is (``callback_mode``
+        "replay"): the kernel logs every collision with its payload, the host replays the log --
+        ``ball_callbacks[i](t, pos, vel_before, vel_after, other ball or obstacle)``,
+        ``obstacle_callbacks[obs](t, pos, vel_before, vel_after, args, ball)``, then ``time_callback(t)``, in the
+        reference's order.  Differences from the reference, by design: callbacks run after the launch, so the
+        billiard's own arrays read inside a callback show the end of the launch (``callback_mode = "step"`` gives one
+        launch per collision and current arrays; in both modes the velocities are already the post-collision ones,
+        whereas the reference calls back just before it stores them).
         """
         if ball_callbacks is not None:
             if not isinstance(ball_callbacks, Mapping):
@@ -500,46 +557,57 @@ class Billiard:
             return (int(res.n_ball_ball), int(res.n_ball_obstacle))
 
         n_bb = n_bo = 0
+        if self.callback_mode == "step":
+            while True:
+                res = self._step(end_time, _lib.BL_ANY, ball_callbacks, obstacle_callbacks)
+                n_bb += int(res.n_ball_ball)
+                n_bo += int(res.n_ball_obstacle)
+                if res.n_ball_ball + res.n_ball_obstacle == 0:
+                    break
+                if time_callback is not None:
+                    time_callback(self._time)
+            self._time = end_time
+            return (n_bb, n_bo)
+
+        want_payload = bool(ball_callbacks) or bool(obstacle_callbacks)
+        self._flush()
+        cap, d, hbuf, log = self._log_buffers(int(self.callback_log_capacity))
+        if not want_payload:
+            log = _lib.BlLog(cap, log.t, log.i, log.j, 0)
         while True:
-            res = self._step(end_time, _lib.BL_ANY, ball_callbacks, obstacle_callbacks)
+            res = self._run(end_time, log=log)
             n_bb += int(res.n_ball_ball)
             n_bo += int(res.n_ball_obstacle)
-            if res.n_ball_ball + res.n_ball_obstacle == 0:
+            t, i, j, p = self._read_log(int(res.n_logged), cap, d, hbuf, want_payload)
+            after = self._time
+            try:
+                for e in range(len(t)):
+                    te = float(t[e])
+                    self._time = te  # the reference's `time` while the callbacks of this collision run
+                    if want_payload:
+                        self._call_back(te, int(i[e]), int(j[e]), p[e], ball_callbacks, obstacle_callbacks)
+                    if time_callback is not None:
+                        time_callback(te)
+            finally:
+                self._time = after
+            if res.stop != _lib.BL_STOP_LOG:
                 break
-            if time_callback is not None:
-                time_callback(self._time)
-        self._time = end_time
+        if res.stop == _lib.BL_STOP_TIME:
+            self._time = end_time
         return (n_bb, n_bo)
 
     def _step(self, end_time, kind, ball_callbacks, obstacle_callbacks):
-        """One collision with its callback payload (the device logs pos / v_before / v_after of the event)."""
-        import torch
-        h = self._h()
-        dev = h.torch_device
+        """One collision with its callback payload (the device logs pos / v_before / v_after of the event); the
+        record comes back through one pinned block."""
         want = bool(ball_callbacks) or bool(obstacle_callbacks)
         log = None
         if want:
-            buf_t = torch.zeros(1, dtype=torch.float64, device=dev)
-            buf_ij = torch.zeros(2, dtype=torch.int64, device=dev)
-            buf_p = torch.zeros(12, dtype=torch.float64, device=dev)
-            log = _lib.BlLog(1, buf_t.data_ptr(), buf_ij[0:].data_ptr(), buf_ij[1:].data_ptr(), buf_p.data_ptr())
+            self._flush()
+            cap, d, hbuf, log = self._log_buffers(1)
         res = self._run(end_time, max_events=1, first_kind=kind, log=log)
         if want and res.n_logged:
-            t = float(buf_t.item())
-            i, j = buf_ij.cpu().tolist()
-            p = buf_p.cpu().numpy()
-            if j >= 0:
-                if ball_callbacks:
-                    if i in ball_callbacks:
-                        ball_callbacks[i](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), j)
-                    if j in ball_callbacks:
-                        ball_callbacks[j](t, p[6:8].copy(), p[8:10].copy(), p[10:12].copy(), i)
-            else:
-                obs, args = self._obs_and_args(-1 - j, p[6])
-                if ball_callbacks and i in ball_callbacks:
-                    ball_callbacks[i](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), obs)
-                if obstacle_callbacks and obs in obstacle_callbacks:
-                    obstacle_callbacks[obs](t, p[0:2].copy(), p[2:4].copy(), p[4:6].copy(), args, i)
+            t, i, j, p = self._read_log(1, cap, d, hbuf)
+            self._call_back(float(t[0]), int(i[0]), int(j[0]), p[0], ball_callbacks, obstacle_callbacks)
         return res
 
     def bounce_ball_ball(self, ball_callbacks=None):

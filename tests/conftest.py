@@ -11,6 +11,10 @@ for p in (ROOT, os.path.join(ROOT, "python-billiards_b200")):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# tests/golden/ref_tests/ holds the reference's own test files; they are run in a subprocess by
+# tests/test_gpu_reference_suite.py (their import sets numpy's error state), never collected into this session
+collect_ignore = [] if os.environ.get("BILLIARDS_COLLECT_REF_TESTS") else ["golden"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

@@ -64,7 +64,57 @@ def pool_ensemble(S, reps=3):
                       "collisions_per_s": total / (ms * 1e-3)}), flush=True)
 
 
+def pool_with_callbacks(reps=5):
+    """f1: the whole pool run (415 collisions) with a callback on every ball, every wall and the clock"""
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.pool()
+    best = None
+    for mode in ("replay", "step"):
+        for _ in range(reps if mode == "replay" else 1):
+            bld = billiards.Billiard(workloads.make_obstacles(billiards, cfg.obstacles), dot_fma=fma)
+            bld.callback_mode = mode
+            bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
+            bld._flush()
+            calls = [0]
+
+            def cb(*a):
+                calls[0] += 1
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c = bld.evolve(100.0, time_callback=cb, ball_callbacks={i: cb for i in range(16)},
+                           obstacle_callbacks={o: cb for o in bld.obstacles})
+            wall = time.perf_counter() - t0
+            if best is None or wall < best:
+                best = wall
+        print(json.dumps({"workload": f"pool_callbacks_{mode}", "counts": c, "callbacks": calls[0], "wall_ms": best * 1e3}),
+              flush=True)
+        best = None
+
+
+def frame_loop(frames=600):
+    """what visualize_matplotlib.animate / the pyglet window do: many short evolve calls + a read of the positions"""
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.ideal_gas()
+    bld = billiards.Billiard(workloads.make_obstacles(billiards, cfg.obstacles), dot_fma=fma)
+    bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
+    bld.evolve(0.05)
+    _ = bld.balls_position
+    torch.cuda.synchronize()
+    dt = 1.0 / 60.0
+    t0 = time.perf_counter()
+    n = 0
+    for k in range(frames):
+        c = bld.evolve(0.05 + (k + 1) * dt)
+        pos = bld.balls_position
+        n += sum(c)
+    wall = time.perf_counter() - t0
+    print(json.dumps({"workload": "frame_loop_ideal_gas_1024", "frames": frames, "collisions": n,
+                      "frames_per_s": frames / wall, "ms_per_frame": wall / frames * 1e3}), flush=True)
+
+
 if __name__ == "__main__":
+    pool_with_callbacks()
+    frame_loop()
     single(workloads.galperin(), 16.0)
     single(workloads.pool(), 100.0)
     single(workloads.newtons_cradle(5, True), 50.0)
