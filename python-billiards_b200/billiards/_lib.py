@@ -98,6 +98,7 @@ SIGNATURES = {
                                         c_void]),
     "bl_multi_run": (ctypes.c_int, [_H, ctypes.POINTER(BlMulti), ctypes.c_int, ctypes.c_double, ctypes.c_int64, c_void]),
     "bl_multi_positions": (ctypes.c_int, [_H, ctypes.POINTER(BlMulti), ctypes.c_double, ctypes.c_int, c_void, c_void]),
+    "bl_measure_fp64_peak": (ctypes.c_int, [_H, c_double_p, c_void]),
     "bl_last_kernel_ms": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_float)]),
     "bl_launch_count": (ctypes.c_int64, [_H]),
     "bl_evolve_config": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
@@ -220,6 +221,11 @@ class Handle:
 
     def launch_count(self):
         return int(self.lib.bl_launch_count(self.h))
+
+    def fp64_peak_tflops(self):
+        x = ctypes.c_double()
+        self.check(self.lib.bl_measure_fp64_peak(self.h, ctypes.byref(x), self.stream()))
+        return float(x.value)
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -318,6 +318,12 @@ int bl_multi_positions(bl_handle *h, const bl_multi *m, double time, int at_syst
     return bl_launch_multi_positions(h, m, time, at_system_time, d_pos, as_stream(stream));
 }
 
+int bl_measure_fp64_peak(bl_handle *h, double *tflops, void *stream) {
+    if (!h || !tflops) return BL_EINVAL;
+    bl_entry_guard g(h);
+    return bl_launch_fp64_peak(h, tflops, as_stream(stream));
+}
+
 int bl_last_kernel_ms(const bl_handle *h, float *ms) {
     if (!h || !ms) return BL_EINVAL;
     bl_entry_guard g(h);
@@ -344,6 +350,7 @@ int bl_set_cta_shape_limit(bl_handle *h, int max_balls) {
 int bl_set_small_kernel(bl_handle *h, int enable) {
     if (!h) return BL_EINVAL;
     h->small_kernel_off = enable ? 0 : 1;
+    h->small_force_lanes = enable == 2 ? 1 : 0;
     return BL_OK;
 }
 

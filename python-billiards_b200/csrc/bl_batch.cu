@@ -135,3 +135,43 @@ int bl_launch_segment_param(bl_handle *h, bl_obstacle sg, const double *d_in, do
     h->launches++;
     return bl_check_cuda(h, cudaGetLastError(), "launch segment_param_kernel");
 }
+
+// ---- measurement: the FP64 pipe's FMA peak, the denominator of the ensemble kernel's roofline -------------------
+namespace {
+__global__ void __launch_bounds__(256) bl_fp64_peak_kernel(double *out, const double y, const int iters) {
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[u] = (double)(threadIdx.x + u);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] = __fma_rn(a[u], y, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += a[u];
+    if (s == 12345.678) out[0] = s;  // keeps the chain alive, never true
+}
+}  // namespace
+
+int bl_launch_fp64_peak(bl_handle *h, double *tflops, cudaStream_t st) {
+    double *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, 8);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "cudaMalloc");
+    const int iters = 1 << 15, ctas = h->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {  // first one warms up
+        cudaEventRecord(h->ev0, st);
+        bl_fp64_peak_kernel<<<ctas, threads, 0, st>>>(d_out, 0.999999, iters);
+        cudaEventRecord(h->ev1, st);
+        h->launches++;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        if (rep && ms < best) best = ms;
+    }
+    cudaFree(d_out);
+    if (e != cudaSuccess) return bl_check_cuda(h, e, "bl_fp64_peak_kernel");
+    *tflops = 2.0 * 8.0 * iters * (double)ctas * threads / (best * 1e-3) / 1e12;
+    return BL_OK;
+}

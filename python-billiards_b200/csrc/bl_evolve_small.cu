@@ -21,44 +21,11 @@
 // (bounce_ball_obstacle), :556-560 (_move), :562-636 (resolve), :176-209 (add_ball's row, for table builds).
 #include <cstring>
 
-#include "bl_arith.cuh"
-#include "bl_internal.h"
+#include "bl_small.cuh"
+
+using namespace bl_small;
 
 namespace {
-
-enum { KIND_BOTH = 0, KIND_BB = 1, KIND_BO = 2 };
-
-#define BL_SMALL_WARPS 4  // warps per CTA in ensemble launches
-
-struct SmallParams {
-    long long n_sys;
-    int n, K, n_obs;
-    int toi_pitch;             // row pitch of one system's table in doubles
-    long long toi_sys_stride;  // doubles between the tables of consecutive systems
-    double *p0x, *p0y, *vx, *vy, *t0;  // ball i of system s at [s*n + i]
-    const double *radius, *mass;       // [n]
-    const int32_t *rclass;             // [n]
-    const double *rsum2, *rsum2_obs;
-    const bl_obstacle *obstacles;
-    double *toi;
-    double *obs_t, *obs_arg;
-    int32_t *obs_idx;
-    double end_time;
-    long long max_events;
-    // single system only
-    double time;
-    int first_kind, query_only;
-    bl_log log;
-    bl_result *result;
-    double *cover_t;
-    uint64_t *cover_code;
-    int64_t *seq_counter;
-    // ensembles only
-    int build_tables;          // solve every pair at the system's current time first (what add_ball does row by row)
-    double *sys_time;
-    int64_t *n_bb, *n_bo;
-    int32_t *status;
-};
 
 // lexicographic (time, code): numpy's first-index argmin (FP compare, so -0.0 == 0.0 like there) with the pair /
 // obstacle codes of bl_arith.cuh breaking ties
@@ -377,6 +344,8 @@ int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double
     cudaError_t e = cudaMemsetAsync(h->d_result, 0, sizeof(bl_result), st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset result");
     h->launches++;
+    if (P.n <= BL_TINY_MAX_BALLS && !h->small_force_lanes)
+        return bl_check_cuda(h, bl_launch_tiny(P, h->dot_fma != 0, true, h->sm_count, st), "launch bl_evolve_tiny_kernel");
     e = h->dot_fma ? launch_w<true, true>(P, h->sm_count, st) : launch_w<false, true>(P, h->sm_count, st);
     return bl_check_cuda(h, e, "launch bl_evolve_small_kernel");
 }
@@ -396,6 +365,9 @@ int bl_launch_multi(bl_handle *h, const bl_multi *m, int build_tables, double en
     P.build_tables = build_tables;
     P.sys_time = m->time; P.n_bb = m->n_ball_ball; P.n_bo = m->n_ball_obstacle; P.status = m->status;
     h->launches++;
+    if (P.n <= BL_TINY_MAX_BALLS && !h->small_force_lanes)
+        return bl_check_cuda(h, bl_launch_tiny(P, h->dot_fma != 0, false, h->sm_count, st),
+                             "launch bl_evolve_tiny_kernel (ensemble)");
     cudaError_t e = h->dot_fma ? launch_w<true, false>(P, h->sm_count, st) : launch_w<false, false>(P, h->sm_count, st);
     return bl_check_cuda(h, e, "launch bl_evolve_small_kernel (ensemble)");
 }

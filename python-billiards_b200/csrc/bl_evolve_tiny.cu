@@ -1,0 +1,319 @@
+// bl_evolve_tiny.cu -- the event loop for systems of at most FOUR balls, ONE THREAD PER SYSTEM.
+//
+// Galperin's pi-with-pool (two balls and a wall, 314159 strictly serial collisions; README.md:58-63 of the reference)
+// is a pure latency problem: every collision depends on the one before, and there is nothing to spread over lanes --
+// after a ball-ball collision of two balls there is no other pair to re-solve at all.  With one thread per system the
+// whole state (5 doubles per ball, <= 6 pair times, <= 4 obstacle entries) lives in registers, the argmin is a short
+// compare / select tree, and there are no shuffles, no shared-memory table, no warp synchronisation and no divergence:
+// a collision costs the dependent FP64 chain of resolve -> re-solve and little else.
+//
+// Same contract as bl_evolve_small.cu (and therefore as bl_evolve.cu): same arithmetic (bl_arith.cuh), same keys
+// (time, then ball-ball before ball-obstacle, then smallest row / column / ball), same stop rules, same result block.
+// Serves a single Billiard (SINGLE) and ensembles of tiny systems (bl_multi_run with n <= 4: 128 systems per CTA).
+// Reference lines: simulation.py:354-438, :440-502, :504-554, :556-560, :562-636, :176-209.
+#include <cstring>
+
+#include "bl_small.cuh"
+
+using namespace bl_small;
+
+namespace {
+
+template <int N>
+__device__ __forceinline__ double pick(const double (&x)[N], int k) {
+    double r = x[0];
+#pragma unroll
+    for (int q = 1; q < N; q++) r = k == q ? x[q] : r;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ int pick(const int (&x)[N], int k) {
+    int r = x[0];
+#pragma unroll
+    for (int q = 1; q < N; q++) r = k == q ? x[q] : r;
+    return r;
+}
+
+// next obstacle of ball k and (if kb >= 0) of ball kb.  Lists of walls only (Galperin, pool, the gases) take a loop
+// that handles both balls per wall without early exits, so that the two dependent chains (dot, dot, divide) overlap;
+// anything else goes through bl_next_obstacle, one ball after the other.
+template <bool FMA>
+__device__ __forceinline__ void next_obstacle_pair(const bl_obstacle *s_obs, int n_obs, bool walls_only,
+                                                   const double *rsum2_obs, int K, double t, bool two,  //
+                                                   int rc1, double p1x, double p1y, double v1x, double v1y, double r1,
+                                                   double &ot1, int &oi1, double &oa1,                   //
+                                                   int rc2, double p2x, double p2y, double v2x, double v2y, double r2,
+                                                   double &ot2, int &oi2, double &oa2) {
+    if (walls_only) {
+        double m1 = BL_INF, m2 = BL_INF, a1 = 0.0, a2 = 0.0;
+        int q1 = -1, q2 = -1;
+        for (int q = 0; q < n_obs; q++) {
+            const double nx = s_obs[q].c, ny = s_obs[q].d, sx = s_obs[q].a, sy = s_obs[q].b;
+            // obstacles.py:112-133: headway = -(v.n); gap = (p - start).n - radius; t = gap / headway
+            const double h1 = -bl_dot2<FMA>(v1x, v1y, nx, ny), h2 = -bl_dot2<FMA>(v2x, v2y, nx, ny);
+            const double g1 = bl_sub(bl_dot2<FMA>(bl_sub(p1x, sx), bl_sub(p1y, sy), nx, ny), r1);
+            const double g2 = bl_sub(bl_dot2<FMA>(bl_sub(p2x, sx), bl_sub(p2y, sy), nx, ny), r2);
+            const double u1 = bl_div(g1, h1);
+            const bool ok1 = !(h1 <= 0.0) && !(u1 < BL_T_EPS);
+            if (ok1 && u1 < m1) { m1 = u1; q1 = q; a1 = h1; }
+            if (two) {
+                const double u2 = bl_div(g2, h2);
+                const bool ok2 = !(h2 <= 0.0) && !(u2 < BL_T_EPS);
+                if (ok2 && u2 < m2) { m2 = u2; q2 = q; a2 = h2; }
+            }
+        }
+        ot1 = bl_add(t, m1); oi1 = q1; oa1 = a1;
+        if (two) { ot2 = bl_add(t, m2); oi2 = q2; oa2 = a2; }
+        return;
+    }
+    bl_next_obstacle<FMA>(s_obs, n_obs, rsum2_obs, K, rc1, p1x, p1y, v1x, v1y, r1, t, ot1, oi1, oa1);
+    if (two) bl_next_obstacle<FMA>(s_obs, n_obs, rsum2_obs, K, rc2, p2x, p2y, v2x, v2y, r2, t, ot2, oi2, oa2);
+}
+
+template <bool FMA, int N, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_tiny_kernel(const __grid_constant__ SmallParams P) {
+    __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
+    __shared__ int s_walls_only;
+    const int n = P.n, K = P.K, n_obs = P.n_obs;
+    if (threadIdx.x == 0) s_walls_only = 1;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_obs; q += blockDim.x) {
+        s_obs[q] = P.obstacles[q];
+        if (s_obs[q].kind != BL_OBS_WALL) s_walls_only = 0;
+    }
+    __syncthreads();
+    const bool walls_only = s_walls_only != 0;
+    const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= P.n_sys) return;
+    const long long sb = sys * n;
+
+    double p0x[N], p0y[N], vx[N], vy[N], t0[N], mass[N], radius[N], ot[N], oarg[N];
+    int rc[N], oidx[N];
+    double T[N][N];   // T[lo][hi], lo < hi: the pair's absolute impact time (toi_table[hi][lo] of the reference)
+    double rs[N][N];  // (r_lo + r_hi)**2 from the host's table
+    double now = SINGLE ? P.time : P.sys_time[sys];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const bool own = k < n;
+        p0x[k] = own ? P.p0x[sb + k] : 0.0; p0y[k] = own ? P.p0y[sb + k] : 0.0;
+        vx[k] = own ? P.vx[sb + k] : 0.0; vy[k] = own ? P.vy[sb + k] : 0.0; t0[k] = own ? P.t0[sb + k] : 0.0;
+        mass[k] = own ? P.mass[k] : 1.0; radius[k] = own ? P.radius[k] : 0.0; rc[k] = own ? P.rclass[k] : 0;
+        ot[k] = BL_INF; oarg[k] = 0.0; oidx[k] = -1;
+    }
+#pragma unroll
+    for (int hi = 1; hi < N; hi++)
+#pragma unroll
+        for (int lo = 0; lo < hi; lo++) {
+            rs[lo][hi] = P.rsum2[(size_t)rc[lo] * K + rc[hi]];
+            T[lo][hi] = BL_INF;
+        }
+    if (!SINGLE && P.build_tables) {
+        // add_ball, row by row at the current time (simulation.py:176-209)
+        double px[N], py[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { px[k] = bl_advance(p0x[k], vx[k], now, t0[k]); py[k] = bl_advance(p0y[k], vy[k], now, t0[k]); }
+#pragma unroll
+        for (int hi = 1; hi < N; hi++)
+#pragma unroll
+            for (int lo = 0; lo < hi; lo++)
+                if (hi < n)
+                    T[lo][hi] = bl_add(now, bl_toi_ball_ball<FMA>(px[lo], py[lo], vx[lo], vy[lo], px[hi], py[hi], vx[hi],
+                                                                  vy[hi], rs[lo][hi]));
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < n)
+                bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc[k], px[k], py[k], vx[k], vy[k], radius[k], now,
+                                      ot[k], oidx[k], oarg[k]);
+    } else {
+        const double *tab = P.toi + sys * P.toi_sys_stride;
+#pragma unroll
+        for (int hi = 1; hi < N; hi++)
+#pragma unroll
+            for (int lo = 0; lo < hi; lo++)
+                if (hi < n) T[lo][hi] = tab[(size_t)hi * P.toi_pitch + lo];
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < n) { ot[k] = P.obs_t[sb + k]; oarg[k] = P.obs_arg[sb + k]; oidx[k] = P.obs_idx[sb + k]; }
+    }
+
+    const bool want_log = SINGLE && P.log.cap > 0;
+    long long done = 0, n_bb = 0;
+    int kindmask = KIND_BOTH;
+    if (SINGLE) kindmask = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
+    int stop_kind = BL_STOP_TIME, st_status = BL_OK, err_i = -1, err_j = -1;
+    double bb_t, bo_t, t_fail = 0.0;
+    int bb_lo, bb_hi, bo_k;
+
+    for (;;) {
+        // ---- the two minima the reference caches (simulation.py:193-198, :205-209): first index on ties ----
+        bb_t = BL_INF; bb_lo = -1; bb_hi = 0;
+#pragma unroll
+        for (int hi = 1; hi < N; hi++)
+#pragma unroll
+            for (int lo = 0; lo < hi; lo++) {
+                const bool lt = T[lo][hi] < bb_t;
+                bb_t = lt ? T[lo][hi] : bb_t; bb_lo = lt ? lo : bb_lo; bb_hi = lt ? hi : bb_hi;
+            }
+        bo_t = ot[0]; bo_k = 0;
+#pragma unroll
+        for (int k = 1; k < N; k++) {
+            const bool lt = ot[k] < bo_t;
+            bo_t = lt ? ot[k] : bo_t; bo_k = lt ? k : bo_k;
+        }
+        if (SINGLE && P.query_only) break;
+        // a ball-ball collision wins a tie (simulation.py:421)
+        const bool take_bb = kindmask == KIND_BB || (kindmask == KIND_BOTH && bb_lo >= 0 && !(bo_t < bb_t));
+        const double t = take_bb ? bb_t : bo_t;
+        int a = take_bb ? bb_lo : bo_k, b = take_bb ? bb_hi : -1;
+        // Opaque to the optimiser on purpose.  nvcc 12.9 folded pick(x, b) to x[0] in the <N = 2, ensemble> instance
+        // (the PTX used ball 0 for both partners of a ball-ball collision: mass, position and velocity; seen on the
+        // GPU as BL_EDIVZERO and pinned by tests/test_gpu_ensembles.py::test_multi_ball_ensemble_against_oracle[2-1]);
+        // with the indices hidden behind an empty asm every instance selects by the run-time value.
+        asm volatile("" : "+r"(a), "+r"(b));
+
+        // ---- stop rules (same order as bl_evolve_small.cu) ----
+        if (P.max_events >= 0 && done >= P.max_events) { stop_kind = BL_STOP_EVENTS; break; }
+        if (t != t) { stop_kind = BL_STOP_ERROR; st_status = BL_ENAN; err_i = a; err_j = b; t_fail = t; break; }
+        if (!(t <= P.end_time) || !(t < BL_INF) || a < 0) { stop_kind = BL_STOP_TIME; break; }
+        if (want_log && done >= P.log.cap) { stop_kind = BL_STOP_LOG; break; }
+
+        // ---- _move(t) for every ball (simulation.py:556-560), then resolve ----
+        double px[N], py[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { px[k] = bl_advance(p0x[k], vx[k], t, t0[k]); py[k] = bl_advance(p0y[k], vy[k], t, t0[k]); }
+        const double ax = pick(px, a), ay = pick(py, a), a_vx = pick(vx, a), a_vy = pick(vy, a);
+        double avx = a_vx, avy = a_vy, bx = 0, by = 0, b_vx = 0, b_vy = 0, bvx = 0, bvy = 0, qarg = 0;
+        int oi = -1, st;
+        if (b < 0) {
+            oi = pick(oidx, a); qarg = pick(oarg, a);
+            st = oi >= 0 ? bl_obstacle_bounce<FMA>(s_obs[oi], ax, ay, a_vx, a_vy, qarg, avx, avy) : BL_EASSERT;
+        } else {
+            bx = pick(px, b); by = pick(py, b); b_vx = pick(vx, b); b_vy = pick(vy, b);
+            double m1 = pick(mass, a), m2 = pick(mass, b);
+            bl_remap_masses(m1, m2);
+            bvx = b_vx; bvy = b_vy;
+            st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bx, by, b_vx, b_vy, m2, avx, avy, bvx, bvy);
+        }
+        if (st != BL_OK) {
+            // the reference has moved to t and raised; the collision is not applied
+            stop_kind = BL_STOP_ERROR; st_status = st; err_i = a; err_j = b; t_fail = t;
+            break;
+        }
+        // ---- log, simulation.py:590-594 / :626-631 payloads ----
+        if (want_log) {
+            const long long e = done;
+            P.log.t[e] = t; P.log.i[e] = a; P.log.j[e] = b >= 0 ? (long long)b : -1 - (long long)oi;
+            if (P.log.payload) {
+                double *o = P.log.payload + 12 * e;
+                o[0] = ax; o[1] = ay; o[2] = a_vx; o[3] = a_vy; o[4] = avx; o[5] = avy;
+                if (b >= 0) { o[6] = bx; o[7] = by; o[8] = b_vx; o[9] = b_vy; o[10] = bvx; o[11] = bvy; }
+                else { o[6] = qarg; o[7] = 0; o[8] = 0; o[9] = 0; o[10] = 0; o[11] = 0; }
+            }
+        }
+        // ---- new state of record of the colliding balls (:597-602, :634-635) ----
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (k == a) { p0x[k] = ax; p0y[k] = ay; vx[k] = avx; vy[k] = avy; t0[k] = t; }
+            if (k == b) { p0x[k] = bx; p0y[k] = by; vx[k] = bvx; vy[k] = bvy; t0[k] = t; }
+        }
+        // ---- re-solve every pair with a colliding ball (:461-471, :522-526); the colliding pair itself = inf (:458) ----
+#pragma unroll
+        for (int hi = 1; hi < N; hi++)
+#pragma unroll
+            for (int lo = 0; lo < hi; lo++) {
+                const bool inv = lo == a || hi == a || lo == b || hi == b;
+                if (inv && hi < n) {
+                    if (lo == a && hi == b) T[lo][hi] = BL_INF;
+                    else
+                        T[lo][hi] = bl_add(t, bl_toi_ball_ball<FMA>(px[lo], py[lo], vx[lo], vy[lo], px[hi], py[hi], vx[hi],
+                                                                   vy[hi], rs[lo][hi]));
+                }
+            }
+        // ---- next obstacle of the colliding balls (:490-495, :545-547) ----
+        {
+            const int kb = b >= 0 ? b : a;
+            double o1, o2, g1, g2;
+            int i1, i2;
+            next_obstacle_pair<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b >= 0,  //
+                                    pick(rc, a), ax, ay, avx, avy, pick(radius, a), o1, i1, g1,  //
+                                    pick(rc, kb), bx, by, bvx, bvy, pick(radius, kb), o2, i2, g2);
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                if (k == a) { ot[k] = o1; oidx[k] = i1; oarg[k] = g1; }
+                if (k == b) { ot[k] = o2; oidx[k] = i2; oarg[k] = g2; }
+            }
+        }
+        done++;
+        n_bb += b >= 0 ? 1 : 0;
+        now = t;
+        kindmask = KIND_BOTH;  // only the first event's kind was forced
+    }
+
+    // ---- write the state, the table and the caches back ----
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if (k < n) {
+            P.p0x[sb + k] = p0x[k]; P.p0y[sb + k] = p0y[k]; P.vx[sb + k] = vx[k]; P.vy[sb + k] = vy[k];
+            P.t0[sb + k] = t0[k];
+            P.obs_t[sb + k] = ot[k]; P.obs_arg[sb + k] = oarg[k]; P.obs_idx[sb + k] = oidx[k];
+        }
+    {
+        double *tab = P.toi + sys * P.toi_sys_stride;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i >= n) continue;
+            double mt = BL_INF;
+            int mj = -1;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                if (j >= n) continue;
+                const double v = i == j ? BL_INF : (i < j ? T[i][j] : T[j][i]);
+                tab[(size_t)i * P.toi_pitch + j] = v;
+                const bool lt = v < mt;
+                mt = lt ? v : mt; mj = lt ? j : mj;
+            }
+            if (SINGLE) { P.cover_t[i] = mt; P.cover_code[i] = mj >= 0 ? bl_pair_code(i, mj) : BL_CODE_NONE; }
+        }
+    }
+    if (SINGLE) {
+        bl_result *const res = P.result;
+        double tnow = now;
+        if (st_status != BL_OK) tnow = t_fail;
+        if (stop_kind == BL_STOP_TIME && P.end_time < BL_INF) tnow = P.end_time;  // _move(end_time), :436
+        if (P.query_only) { tnow = P.time; stop_kind = BL_STOP_TIME; }
+        res->time = tnow; res->stop = stop_kind; res->status = st_status;
+        res->err_i = err_i; res->err_j = err_j;
+        res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb; res->n_logged = want_log ? done : 0;
+        const bool some = bb_lo >= 0 && bb_t < BL_INF;
+        res->bb_t = some ? bb_t : BL_INF; res->bb_i = some ? bb_lo : -1; res->bb_j = some ? bb_hi : 0;
+        // numpy argmin over _obstacles_toi: first ball attaining the minimum, even when it is +inf
+        res->bo_t = bo_t; res->bo_ball = bo_k; res->bo_obs = pick(oidx, bo_k); res->bo_arg = pick(oarg, bo_k);
+        for (int q = 0; q < 16; q++) res->prof[q] = 0;
+        res->prof[5] = done;
+        res->window = 0.0;
+        *P.seq_counter += done;
+    } else {
+        P.sys_time[sys] = st_status != BL_OK ? t_fail
+                          : ((stop_kind == BL_STOP_TIME && P.end_time < BL_INF) ? P.end_time : now);
+        P.n_bb[sys] += n_bb; P.n_bo[sys] += done - n_bb;
+        P.status[sys] = st_status;
+    }
+}
+
+template <bool FMA, bool SINGLE>
+cudaError_t launch_n(const SmallParams &P, cudaStream_t st) {
+    const unsigned grid = SINGLE ? 1u : (unsigned)((P.n_sys + 127) / 128);
+    const unsigned block = SINGLE ? 32u : 128u;
+    if (P.n <= 2) bl_evolve_tiny_kernel<FMA, 2, SINGLE><<<grid, block, 0, st>>>(P);
+    else bl_evolve_tiny_kernel<FMA, 4, SINGLE><<<grid, block, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t bl_launch_tiny(const SmallParams &P, bool fma, bool single, int sm_count, cudaStream_t st) {
+    (void)sm_count;
+    if (P.n < 1 || P.n > BL_TINY_MAX_BALLS) return cudaErrorInvalidValue;
+    if (fma) return single ? launch_n<true, true>(P, st) : launch_n<true, false>(P, st);
+    return single ? launch_n<false, true>(P, st) : launch_n<false, false>(P, st);
+}

@@ -33,6 +33,7 @@ struct bl_handle {
     const void *window_sys;
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
     int small_kernel_off;     // bl_set_small_kernel(h, 0): systems of <= 32 balls also take the grid-wide event kernel
+    int small_force_lanes;    // bl_set_small_kernel(h, 2): systems of <= 4 balls take the lane-group kernel, not the one-thread kernel
     int ensemble_generic;     // BL_ENSEMBLE_GENERIC=1: always use the generic (list in shared memory) ensemble kernel
     char err[512];
 };
@@ -48,6 +49,7 @@ struct bl_handle {
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
 #define BL_SMALL_MAX_BALLS 32  // systems up to this size run in the one-warp kernel (bl_evolve_small.cu)
 #define BL_SMALL_MAX_OBS 32
+#define BL_TINY_MAX_BALLS 4    // systems up to this size run one thread per system (bl_evolve_tiny.cu)
 #define BL_HL_CAP 6           // finite new values of one ball listed per round (more -> that ball scans all of them)
 #define BL_RCHUNK 256         // stale candidates repaired per pass
 #define BL_STASH_BYTES 98304  // shared memory for the parked pair solutions of a round
@@ -109,6 +111,7 @@ int bl_launch_point_batch(bl_handle *h, const double *d_in, const double *d_r2, 
                           cudaStream_t st);
 int bl_launch_segment_param(bl_handle *h, bl_obstacle sg, const double *d_in, double t_eps, double *d_t, double *d_u,
                             int32_t *d_code, long long m, cudaStream_t st);
+int bl_launch_fp64_peak(bl_handle *h, double *tflops, cudaStream_t st);
 // bl_ensemble.cu
 int bl_launch_ensemble(bl_handle *h, const bl_obstacle *obs, int n_obs, const double *rsum2_obs, double radius,
                        long long n_sys, double *d_state, double *d_time, long long n_coll, double end_time,

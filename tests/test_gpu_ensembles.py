@@ -204,21 +204,30 @@ def _small_gas(rng, n, S):
     return obstacles, pos, vel, radius, mass
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 16, 17, 31, 32])
-def test_multi_ball_ensemble_against_oracle(billiards, oracle, n):
-    """S systems x n balls, one group of W lanes per system: evolve(T/2) + evolve(T) + run(count) == the oracle's
-    evolve on each system, bit for bit (state, clocks, counts, the whole time-of-impact table)."""
+@pytest.mark.parametrize("n,kernel", [(1, 1), (2, 1), (3, 1), (4, 1), (1, 2), (2, 2), (3, 2), (4, 2), (5, 1), (8, 1),
+                                      (9, 1), (16, 1), (17, 1), (31, 1), (32, 1)])
+def test_multi_ball_ensemble_against_oracle(billiards, oracle, n, kernel):
+    """S systems x n balls -- one thread per system up to 4 balls (kernel 1) or one group of W lanes per system
+    (kernel 2 forces it for n <= 4 too): evolve(T/2) + evolve(T) + run(count) == the oracle's evolve on each system,
+    bit for bit (state, clocks, counts, the whole time-of-impact table)."""
     from billiards import _lib
     fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
     rng = np.random.default_rng(50 + n)
-    S = 37
+    S = 37 if n > 4 else 150
     obstacles, pos, vel, radius, mass = _small_gas(rng, n, S)
+    if n <= 4 and kernel == 1:
+        obstacles = obstacles[:4]  # walls only: the one-thread kernel's two-balls-per-wall loop
     ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, radius=radius, mass=mass,
                                      dot_fma=fma)
     T = 12.0
-    c1 = ens.evolve(T / 2)
-    c2 = ens.evolve(T)
-    ens.run(25)
+    h.check(h.lib.bl_set_small_kernel(h.h, kernel))
+    try:
+        c1 = ens.evolve(T / 2)
+        c2 = ens.evolve(T)
+        ens.run(25)
+    finally:
+        h.check(h.lib.bl_set_small_kernel(h.h, 1))
     refs = _oracle_systems(oracle, obstacles, pos, vel, radius, mass, fma)
     got_t, got_v, got_p0, got_pos = ens.time, ens.balls_velocity, ens.balls_initial_position, ens.balls_position
     got_bb, got_bo, tables = ens.counts_ball_ball, ens.counts_ball_obstacle, ens.toi_tables

@@ -416,6 +416,35 @@ def test_small_systems_through_the_grid_kernel(billiards, golden):
         h.check(h.lib.bl_set_small_kernel(h.h, 1))
 
 
+def test_tiny_systems_through_the_lane_group_kernel(billiards, golden):
+    """Systems of <= 4 balls normally run one thread per system (bl_evolve_tiny.cu); the lane-group kernel with 2 / 4
+    lanes per system must give the same bits: Galperin's log and total, Newton's cradle with 4 balls."""
+    from billiards import _lib
+    gg = golden("galperin")
+    fma = bool(gg["dot_fma"])
+    h = _lib.get_handle(None, fma)
+    runs = {}
+    for mode in (1, 2):
+        h.check(h.lib.bl_set_small_kernel(h.h, mode))
+        try:
+            gal = build(billiards, workloads.galperin(), fma)
+            _, (t, i, j, p) = gal.evolve_events(20000, log_capacity=20000, payload=True)
+            assert_bits_equal(t, gg["log_t"])
+            assert i.tolist() == gg["log_i"].tolist() and j.tolist() == gg["log_j"].tolist()
+            assert gal.evolve(16) == (157080 - int((gg["log_j"] >= 0).sum()), 157079 - int((gg["log_j"] < 0).sum()))
+            assert gal.next_ball_ball_collision == (INF, -1, 0) and gal.next_ball_obstacle_collision == (INF, 0, None)
+            cr = build(billiards, workloads.newtons_cradle(4, True), fma)
+            c = cr.evolve(40.0, time_callback=lambda t: None)
+            runs[mode] = (p, gal.balls_velocity.copy(), gal.balls_position.copy(), c, cr.balls_position.copy(),
+                          np.concatenate(cr.toi_table), cr._balls_toi.copy(), cr._obstacles_toi.copy(), cr.next_collision[0])
+        finally:
+            h.check(h.lib.bl_set_small_kernel(h.h, 1))
+    a, b = runs[1], runs[2]
+    assert a[3] == b[3] and a[8] == b[8]
+    for q in (0, 1, 2, 4, 5, 6, 7):
+        assert_bits_equal(a[q], b[q], f"item {q}")
+
+
 def test_stop_resume_is_bit_stable(billiards, oracle):
     """tests/test_simulation.py:461-502: 300 partial evolves == one evolve, exactly; and == the oracle."""
     from billiards import _lib
