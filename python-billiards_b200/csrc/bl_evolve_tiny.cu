@@ -165,10 +165,11 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_tiny_kernel(const
         const bool take_bb = kindmask == KIND_BB || (kindmask == KIND_BOTH && bb_lo >= 0 && !(bo_t < bb_t));
         const double t = take_bb ? bb_t : bo_t;
         int a = take_bb ? bb_lo : bo_k, b = take_bb ? bb_hi : -1;
-        // Opaque to the optimiser on purpose.  nvcc 12.9 folded pick(x, b) to x[0] in the <N = 2, ensemble> instance
-        // (the PTX used ball 0 for both partners of a ball-ball collision: mass, position and velocity; seen on the
-        // GPU as BL_EDIVZERO and pinned by tests/test_gpu_ensembles.py::test_multi_ball_ensemble_against_oracle[2-1]);
-        // with the indices hidden behind an empty asm every instance selects by the run-time value.
+        // Opaque to the optimiser on purpose.  nvcc 12.9 folded pick(x, b) to x[0] in the <N = 2, ensemble> instance of
+        // this kernel (the PTX used ball 0 for both partners of a ball-ball collision: mass, position and velocity;
+        // seen on the GPU as BL_EDIVZERO in tests/test_gpu_ensembles.py::test_multi_ball_ensemble_against_oracle[2-1]).
+        // With the indices hidden behind an empty asm every instance selects by the run-time value.  (Systems of one
+        // or two balls have since moved to bl_evolve_pair_kernel below; the guard stays.)
         asm volatile("" : "+r"(a), "+r"(b));
 
         // ---- stop rules (same order as bl_evolve_small.cu) ----
@@ -300,11 +301,250 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_tiny_kernel(const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Systems of ONE or TWO balls (Galperin): the same loop with every ball index resolved by control flow instead of
+// select chains -- a ball-ball collision can only be (0, 1), an obstacle collision is "ball `me` against the list,
+// then the pair with `other`" with the two roles passed by reference.  One thread per system, 314159 strictly serial
+// collisions: what counts is the number of dependent instructions per collision (ncu on the generic instance above:
+// 462 instructions and 1720 cycles per collision, ~150 of them FP64).
+struct Ball {
+    double p0x, p0y, vx, vy, t0, mass, radius, ot, oarg;
+    int rc, oidx;
+};
+
+// IEEE quotient with a shortcut for an exactly-zero numerator over a finite, non-zero denominator: +-0 with the
+// sign of the operands (what __ddiv_rn returns, but through its slow path: ~60 extra instructions).  Galperin's
+// motion is one-dimensional, so every y-component of its impulses is such a quotient.
+__device__ __forceinline__ double div_zero_num(double num, double den) {
+    if (num == 0.0 && den == den && den != 0.0)
+        return __hiloint2double((__double2hiint(num) ^ __double2hiint(den)) & 0x80000000, 0);
+    return bl_div(num, den);
+}
+
+// physics.py:273-282 like bl_elastic, with the two quotients through div_zero_num
+template <bool FMA>
+__device__ __forceinline__ int elastic_pair(double p1x, double p1y, double v1x, double v1y, double m1, double p2x,
+                                            double p2y, double v2x, double v2y, double m2, double &w1x, double &w1y,
+                                            double &w2x, double &w2y) {
+    const double pdx = bl_sub(p2x, p1x), pdy = bl_sub(p2y, p1y);
+    const double vdx = bl_sub(v2x, v1x), vdy = bl_sub(v2y, v1y);
+    const double pdv = bl_dot2<FMA>(pdx, pdy, vdx, vdy);
+    if (pdv > BL_SEP_EPS) return BL_ESEPARATING;
+    const double den = bl_mul(bl_add(m1, m2), bl_dot2<FMA>(pdx, pdy, pdx, pdy));
+    if (den == 0.0) return BL_EDIVZERO;
+    const double ix = div_zero_num(bl_mul(2.0, bl_mul(pdv, pdx)), den);
+    const double iy = div_zero_num(bl_mul(2.0, bl_mul(pdv, pdy)), den);
+    w1x = bl_add(v1x, bl_mul(m2, ix));
+    w1y = bl_add(v1y, bl_mul(m2, iy));
+    w2x = bl_sub(v2x, bl_mul(m1, ix));
+    w2y = bl_sub(v2y, bl_mul(m1, iy));
+    return BL_OK;
+}
+
+// next obstacle of one ball whose state of record was just re-based at time t (simulation.py:332-352)
+template <bool FMA>
+__device__ __forceinline__ void next_obstacle_ball(const bl_obstacle *s_obs, int n_obs, bool walls_only,
+                                                   const double *rsum2_obs, int K, double t, Ball &B) {
+    if (walls_only) {
+        double m = BL_INF, arg = 0.0;
+        int qm = -1;
+#pragma unroll 1
+        for (int q = 0; q < n_obs; q++) {
+            const double nx = s_obs[q].c, ny = s_obs[q].d;
+            const double h = -bl_dot2<FMA>(B.vx, B.vy, nx, ny);
+            if (h <= 0.0) continue;  // moving away from this wall (obstacles.py:117-118)
+            const double g = bl_sub(bl_dot2<FMA>(bl_sub(B.p0x, s_obs[q].a), bl_sub(B.p0y, s_obs[q].b), nx, ny), B.radius);
+            const double u = bl_div(g, h);
+            if (!(u < BL_T_EPS) && u < m) { m = u; qm = q; arg = h; }
+        }
+        B.ot = bl_add(t, m); B.oidx = qm; B.oarg = arg;
+        return;
+    }
+    bl_next_obstacle<FMA>(s_obs, n_obs, rsum2_obs, K, B.rc, B.p0x, B.p0y, B.vx, B.vy, B.radius, t, B.ot, B.oidx, B.oarg);
+}
+
+// one obstacle collision of `me` at time t (simulation.py:504-554 with N <= 2); returns a bl_status
+template <bool FMA>
+__device__ __forceinline__ int obstacle_event(const bl_obstacle *s_obs, int n_obs, bool walls_only,
+                                              const double *rsum2_obs, int K, bool two, double rs01, double t, Ball &me,
+                                              const Ball &other, double &T01, double *payload) {
+    const double ax = bl_advance(me.p0x, me.vx, t, me.t0), ay = bl_advance(me.p0y, me.vy, t, me.t0);
+    double wx = me.vx, wy = me.vy;
+    const int oi = me.oidx;
+    if (oi < 0) return BL_EASSERT;
+    int st = BL_OK;
+    if (walls_only) {  // InfiniteWall.resolve_collision, obstacles.py:135-144
+        wx = bl_add(me.vx, bl_mul(2.0, bl_mul(me.oarg, s_obs[oi].c)));
+        wy = bl_add(me.vy, bl_mul(2.0, bl_mul(me.oarg, s_obs[oi].d)));
+    } else {
+        st = bl_obstacle_bounce<FMA>(s_obs[oi], ax, ay, me.vx, me.vy, me.oarg, wx, wy);
+        if (st != BL_OK) return st;
+    }
+    if (payload) {
+        payload[0] = ax; payload[1] = ay; payload[2] = me.vx; payload[3] = me.vy; payload[4] = wx; payload[5] = wy;
+        payload[6] = me.oarg; payload[7] = 0; payload[8] = 0; payload[9] = 0; payload[10] = 0; payload[11] = 0;
+    }
+    me.p0x = ax; me.p0y = ay; me.vx = wx; me.vy = wy; me.t0 = t;
+    if (two) {  // the one pair of the system is re-solved (:522-526)
+        const double ox = bl_advance(other.p0x, other.vx, t, other.t0), oy = bl_advance(other.p0y, other.vy, t, other.t0);
+        T01 = bl_add(t, bl_toi_ball_ball<FMA>(ax, ay, wx, wy, ox, oy, other.vx, other.vy, rs01));
+    }
+    next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, rsum2_obs, K, t, me);
+    return st;
+}
+
+template <bool FMA, bool SINGLE>
+__global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const __grid_constant__ SmallParams P) {
+    __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
+    __shared__ int s_walls_only;
+    const int n = P.n, K = P.K, n_obs = P.n_obs;
+    if (threadIdx.x == 0) s_walls_only = 1;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_obs; q += blockDim.x) {
+        s_obs[q] = P.obstacles[q];
+        if (s_obs[q].kind != BL_OBS_WALL) s_walls_only = 0;
+    }
+    __syncthreads();
+    const bool walls_only = s_walls_only != 0;
+    const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sys >= P.n_sys) return;
+    const long long sb = sys * n;
+    const bool two = n == 2;
+
+    Ball b0, b1;
+    b0.p0x = P.p0x[sb]; b0.p0y = P.p0y[sb]; b0.vx = P.vx[sb]; b0.vy = P.vy[sb]; b0.t0 = P.t0[sb];
+    b0.mass = P.mass[0]; b0.radius = P.radius[0]; b0.rc = P.rclass[0];
+    b0.ot = BL_INF; b0.oarg = 0.0; b0.oidx = -1;
+    b1 = b0;
+    b1.p0x = 0.0; b1.p0y = 0.0; b1.vx = 0.0; b1.vy = 0.0; b1.t0 = 0.0; b1.mass = 1.0; b1.radius = 0.0; b1.rc = 0;
+    if (two) {
+        b1.p0x = P.p0x[sb + 1]; b1.p0y = P.p0y[sb + 1]; b1.vx = P.vx[sb + 1]; b1.vy = P.vy[sb + 1]; b1.t0 = P.t0[sb + 1];
+        b1.mass = P.mass[1]; b1.radius = P.radius[1]; b1.rc = P.rclass[1];
+    }
+    const double rs01 = P.rsum2[(size_t)b0.rc * K + b1.rc];
+    double T01 = BL_INF;
+    double now = SINGLE ? P.time : P.sys_time[sys];
+    double *const tab = P.toi + sys * P.toi_sys_stride;
+    if (!SINGLE && P.build_tables) {
+        // add_ball, row by row at the current time (simulation.py:176-209)
+        const double x0 = bl_advance(b0.p0x, b0.vx, now, b0.t0), y0 = bl_advance(b0.p0y, b0.vy, now, b0.t0);
+        bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, b0.rc, x0, y0, b0.vx, b0.vy, b0.radius, now, b0.ot, b0.oidx, b0.oarg);
+        if (two) {
+            const double x1 = bl_advance(b1.p0x, b1.vx, now, b1.t0), y1 = bl_advance(b1.p0y, b1.vy, now, b1.t0);
+            T01 = bl_add(now, bl_toi_ball_ball<FMA>(x0, y0, b0.vx, b0.vy, x1, y1, b1.vx, b1.vy, rs01));
+            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, b1.rc, x1, y1, b1.vx, b1.vy, b1.radius, now, b1.ot, b1.oidx, b1.oarg);
+        }
+    } else {
+        b0.ot = P.obs_t[sb]; b0.oarg = P.obs_arg[sb]; b0.oidx = P.obs_idx[sb];
+        if (two) {
+            b1.ot = P.obs_t[sb + 1]; b1.oarg = P.obs_arg[sb + 1]; b1.oidx = P.obs_idx[sb + 1];
+            T01 = tab[P.toi_pitch];
+        }
+    }
+
+    const bool want_log = SINGLE && P.log.cap > 0;
+    long long done = 0, n_bb = 0;
+    int kind = KIND_BOTH;
+    if (SINGLE) kind = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
+    // why the loop ended: 0 time, 1 events, 2 log, 3 NaN time, 4 collision not resolvable (status in st)
+    int why = 0, st = BL_OK, a = -1, b = -1;
+    double t = now;
+    bool o1 = false;
+    if (!(SINGLE && P.query_only)) {
+        for (;;) {
+            // next_ball_ball_collision / next_ball_obstacle_collision: first ball on ties, ball-ball wins a tie
+            o1 = b1.ot < b0.ot;
+            const double bo_t = o1 ? b1.ot : b0.ot;
+            const bool take_bb = kind == KIND_BB || (kind == KIND_BOTH && T01 < BL_INF && !(bo_t < T01));
+            t = take_bb ? T01 : bo_t;
+            if (P.max_events >= 0 && done >= P.max_events) { why = 1; break; }
+            if (t != t) { why = 3; a = take_bb ? 0 : (int)o1; b = take_bb ? 1 : -1; break; }
+            if (!(t <= P.end_time) || !(t < BL_INF)) break;
+            if (want_log && done >= P.log.cap) { why = 2; break; }
+            double *payload = nullptr;
+            if (want_log) {
+                P.log.t[done] = t;
+                if (P.log.payload) payload = P.log.payload + 12 * done;
+            }
+            if (take_bb) {
+                // bounce_ball_ball, simulation.py:440-502 with N = 2: nothing else to re-solve
+                const double ax = bl_advance(b0.p0x, b0.vx, t, b0.t0), ay = bl_advance(b0.p0y, b0.vy, t, b0.t0);
+                const double bx = bl_advance(b1.p0x, b1.vx, t, b1.t0), by = bl_advance(b1.p0y, b1.vy, t, b1.t0);
+                double m1 = b0.mass, m2 = b1.mass;
+                bl_remap_masses(m1, m2);
+                double avx = b0.vx, avy = b0.vy, bvx = b1.vx, bvy = b1.vy;
+                st = elastic_pair<FMA>(ax, ay, b0.vx, b0.vy, m1, bx, by, b1.vx, b1.vy, m2, avx, avy, bvx, bvy);
+                if (st != BL_OK) { why = 4; a = 0; b = 1; break; }
+                if (want_log) {
+                    P.log.i[done] = 0; P.log.j[done] = 1;
+                    if (payload) {
+                        payload[0] = ax; payload[1] = ay; payload[2] = b0.vx; payload[3] = b0.vy; payload[4] = avx; payload[5] = avy;
+                        payload[6] = bx; payload[7] = by; payload[8] = b1.vx; payload[9] = b1.vy; payload[10] = bvx; payload[11] = bvy;
+                    }
+                }
+                b0.p0x = ax; b0.p0y = ay; b0.vx = avx; b0.vy = avy; b0.t0 = t;
+                b1.p0x = bx; b1.p0y = by; b1.vx = bvx; b1.vy = bvy; b1.t0 = t;
+                T01 = BL_INF;  // :458
+                next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b0);
+                next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b1);
+                n_bb++;
+            } else {
+                if (want_log) { P.log.i[done] = (int)o1; P.log.j[done] = -1 - (long long)(o1 ? b1.oidx : b0.oidx); }
+                st = o1 ? obstacle_event<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, two, rs01, t, b1, b0, T01, payload)
+                        : obstacle_event<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, two, rs01, t, b0, b1, T01, payload);
+                if (st != BL_OK) { why = 4; a = (int)o1; b = -1; break; }
+            }
+            done++;
+            now = t;
+            kind = KIND_BOTH;  // only the first event's kind was forced
+        }
+    }
+    o1 = b1.ot < b0.ot;
+
+    // ---- write the state, the table and the caches back ----
+    P.p0x[sb] = b0.p0x; P.p0y[sb] = b0.p0y; P.vx[sb] = b0.vx; P.vy[sb] = b0.vy; P.t0[sb] = b0.t0;
+    P.obs_t[sb] = b0.ot; P.obs_arg[sb] = b0.oarg; P.obs_idx[sb] = b0.oidx;
+    tab[0] = BL_INF;
+    if (two) {
+        P.p0x[sb + 1] = b1.p0x; P.p0y[sb + 1] = b1.p0y; P.vx[sb + 1] = b1.vx; P.vy[sb + 1] = b1.vy; P.t0[sb + 1] = b1.t0;
+        P.obs_t[sb + 1] = b1.ot; P.obs_arg[sb + 1] = b1.oarg; P.obs_idx[sb + 1] = b1.oidx;
+        tab[1] = T01; tab[P.toi_pitch] = T01; tab[P.toi_pitch + 1] = BL_INF;
+    }
+    const bool failed = why >= 3;
+    const int status = why == 3 ? (int)BL_ENAN : (why == 4 ? st : (int)BL_OK);
+    if (SINGLE) {
+        const bool some = T01 < BL_INF;
+        P.cover_t[0] = T01; P.cover_code[0] = some ? bl_pair_code(0, 1) : BL_CODE_NONE;
+        if (two) { P.cover_t[1] = T01; P.cover_code[1] = some ? bl_pair_code(0, 1) : BL_CODE_NONE; }
+        bl_result *const res = P.result;
+        double tnow = failed ? t : now;
+        if (why == 0 && P.end_time < BL_INF) tnow = P.end_time;  // _move(end_time), :436
+        if (P.query_only) tnow = P.time;
+        res->time = tnow;
+        res->stop = failed ? BL_STOP_ERROR : (why == 1 ? BL_STOP_EVENTS : (why == 2 ? BL_STOP_LOG : BL_STOP_TIME));
+        res->status = status;
+        res->err_i = failed ? a : -1; res->err_j = failed ? b : -1;
+        res->n_ball_ball = n_bb; res->n_ball_obstacle = done - n_bb; res->n_logged = want_log ? done : 0;
+        res->bb_t = some ? T01 : BL_INF; res->bb_i = some ? 0 : -1; res->bb_j = some ? 1 : 0;
+        // numpy argmin over _obstacles_toi: first ball attaining the minimum, even when it is +inf
+        res->bo_t = o1 ? b1.ot : b0.ot; res->bo_ball = (int)o1;
+        res->bo_obs = o1 ? b1.oidx : b0.oidx; res->bo_arg = o1 ? b1.oarg : b0.oarg;
+        for (int q = 0; q < 16; q++) res->prof[q] = 0;
+        res->prof[5] = done;
+        res->window = 0.0;
+        *P.seq_counter += done;
+    } else {
+        P.sys_time[sys] = failed ? t : ((why == 0 && P.end_time < BL_INF) ? P.end_time : now);
+        P.n_bb[sys] += n_bb; P.n_bo[sys] += done - n_bb;
+        P.status[sys] = status;
+    }
+}
+
 template <bool FMA, bool SINGLE>
 cudaError_t launch_n(const SmallParams &P, cudaStream_t st) {
     const unsigned grid = SINGLE ? 1u : (unsigned)((P.n_sys + 127) / 128);
     const unsigned block = SINGLE ? 32u : 128u;
-    if (P.n <= 2) bl_evolve_tiny_kernel<FMA, 2, SINGLE><<<grid, block, 0, st>>>(P);
+    if (P.n <= 2) bl_evolve_pair_kernel<FMA, SINGLE><<<grid, block, 0, st>>>(P);
     else bl_evolve_tiny_kernel<FMA, 4, SINGLE><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
 }
