@@ -305,23 +305,23 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_tiny_kernel(const
 // Systems of ONE or TWO balls (Galperin): the same loop with every ball index resolved by control flow instead of
 // select chains -- a ball-ball collision can only be (0, 1), an obstacle collision is "ball `me` against the list,
 // then the pair with `other`" with the two roles passed by reference.  One thread per system, 314159 strictly serial
-// collisions: what counts is the number of dependent instructions per collision (ncu on the generic instance above:
-// 462 instructions and 1720 cycles per collision, ~150 of them FP64).
+// collisions: what counts is the length of the dependent instruction chain per collision (ncu on the generic
+// instance above: 462 instructions and 1720 cycles per collision, ~150 of them FP64).  Hence
+//   * one compare each for the two stop rules (a count limit and a time limit prepared before the loop, held in
+//     registers: re-reading kernel parameters from the constant bank costs ~25 cycles of latency per read);
+//   * the first two walls of a walls-only list live in registers (no shared-memory address arithmetic per collision);
+//   * the two quotients of the impulse share one reciprocal, an exactly-zero numerator (one-dimensional motion: every
+//     y-component) skips the division, and after a ball-ball collision the two balls' wall divisions are interleaved.
 struct Ball {
     double p0x, p0y, vx, vy, t0, mass, radius, ot, oarg;
     int rc, oidx;
 };
+struct Wall {
+    double sx, sy, nx, ny;
+};
 
-// IEEE quotient with a shortcut for an exactly-zero numerator over a finite, non-zero denominator: +-0 with the
-// sign of the operands (what __ddiv_rn returns, but through its slow path: ~60 extra instructions).  Galperin's
-// motion is one-dimensional, so every y-component of its impulses is such a quotient.
-__device__ __forceinline__ double div_zero_num(double num, double den) {
-    if (num == 0.0 && den == den && den != 0.0)
-        return __hiloint2double((__double2hiint(num) ^ __double2hiint(den)) & 0x80000000, 0);
-    return bl_div(num, den);
-}
-
-// physics.py:273-282 like bl_elastic, with the two quotients through div_zero_num
+// physics.py:273-282 like bl_elastic; the quotient of an exactly-zero numerator over a finite non-zero denominator is
+// +-0 with the sign of the operands (what __ddiv_rn returns, but through its slow path)
 template <bool FMA>
 __device__ __forceinline__ int elastic_pair(double p1x, double p1y, double v1x, double v1y, double m1, double p2x,
                                             double p2y, double v2x, double v2y, double m2, double &w1x, double &w1y,
@@ -332,8 +332,12 @@ __device__ __forceinline__ int elastic_pair(double p1x, double p1y, double v1x, 
     if (pdv > BL_SEP_EPS) return BL_ESEPARATING;
     const double den = bl_mul(bl_add(m1, m2), bl_dot2<FMA>(pdx, pdy, pdx, pdy));
     if (den == 0.0) return BL_EDIVZERO;
-    const double ix = div_zero_num(bl_mul(2.0, bl_mul(pdv, pdx)), den);
-    const double iy = div_zero_num(bl_mul(2.0, bl_mul(pdv, pdy)), den);
+    const double nx = bl_mul(2.0, bl_mul(pdv, pdx)), ny = bl_mul(2.0, bl_mul(pdv, pdy));
+    const double r = bl_div_rcp(den);
+    const double ix = bl_div_by(nx, den, r);
+    double iy;
+    if (ny == 0.0 && den == den) iy = __hiloint2double((__double2hiint(ny) ^ __double2hiint(den)) & 0x80000000, 0);
+    else iy = bl_div_by(ny, den, r);
     w1x = bl_add(v1x, bl_mul(m2, ix));
     w1y = bl_add(v1y, bl_mul(m2, iy));
     w2x = bl_sub(v2x, bl_mul(m1, ix));
@@ -341,43 +345,94 @@ __device__ __forceinline__ int elastic_pair(double p1x, double p1y, double v1x, 
     return BL_OK;
 }
 
+// one wall against one ball (obstacles.py:112-133), folded into the running strict minimum
+template <bool FMA>
+__device__ __forceinline__ void wall_fold(const Wall &w, int q, const Ball &B, double &m, int &qm, double &arg) {
+    const double h = -bl_dot2<FMA>(B.vx, B.vy, w.nx, w.ny);
+    if (h <= 0.0) return;  // moving away from this wall (:117-118)
+    const double g = bl_sub(bl_dot2<FMA>(bl_sub(B.p0x, w.sx), bl_sub(B.p0y, w.sy), w.nx, w.ny), B.radius);
+    const double u = bl_div(g, h);
+    if (!(u < BL_T_EPS) && u < m) { m = u; qm = q; arg = h; }
+}
+// the same for two balls at once: both divisions issued side by side (a ball that moves away divides by 1 and is
+// ignored), so that their dependent chains overlap
+template <bool FMA>
+__device__ __forceinline__ void wall_fold2(const Wall &w, int q, const Ball &A, const Ball &B, double &ma, int &qa,
+                                           double &arga, double &mb, int &qb, double &argb) {
+    const double ha = -bl_dot2<FMA>(A.vx, A.vy, w.nx, w.ny), hb = -bl_dot2<FMA>(B.vx, B.vy, w.nx, w.ny);
+    const bool offa = ha <= 0.0, offb = hb <= 0.0;
+    if (offa && offb) return;
+    const double ga = bl_sub(bl_dot2<FMA>(bl_sub(A.p0x, w.sx), bl_sub(A.p0y, w.sy), w.nx, w.ny), A.radius);
+    const double gb = bl_sub(bl_dot2<FMA>(bl_sub(B.p0x, w.sx), bl_sub(B.p0y, w.sy), w.nx, w.ny), B.radius);
+    const double da = offa ? 1.0 : ha, db = offb ? 1.0 : hb;
+    const double ra = bl_div_rcp(da), rb = bl_div_rcp(db);
+    const double ua = bl_div_by(ga, da, ra), ub = bl_div_by(gb, db, rb);
+    if (!offa && !(ua < BL_T_EPS) && ua < ma) { ma = ua; qa = q; arga = ha; }
+    if (!offb && !(ub < BL_T_EPS) && ub < mb) { mb = ub; qb = q; argb = hb; }
+}
+
+struct Obstacles {
+    const bl_obstacle *s_obs;  // the list in shared memory
+    const double *rsum2_obs;
+    Wall w0, w1;               // the first two walls of a walls-only list
+    int n_obs, K;
+    bool walls_only;
+};
+
+__device__ __forceinline__ Wall wall_at(const Obstacles &O, int q) {
+    Wall w;
+    w.sx = O.s_obs[q].a; w.sy = O.s_obs[q].b; w.nx = O.s_obs[q].c; w.ny = O.s_obs[q].d;
+    return w;
+}
+
 // next obstacle of one ball whose state of record was just re-based at time t (simulation.py:332-352)
 template <bool FMA>
-__device__ __forceinline__ void next_obstacle_ball(const bl_obstacle *s_obs, int n_obs, bool walls_only,
-                                                   const double *rsum2_obs, int K, double t, Ball &B) {
-    if (walls_only) {
+__device__ __forceinline__ void next_obstacle_ball(const Obstacles &O, double t, Ball &B) {
+    if (O.walls_only) {
         double m = BL_INF, arg = 0.0;
         int qm = -1;
+        if (O.n_obs > 0) wall_fold<FMA>(O.w0, 0, B, m, qm, arg);
+        if (O.n_obs > 1) wall_fold<FMA>(O.w1, 1, B, m, qm, arg);
 #pragma unroll 1
-        for (int q = 0; q < n_obs; q++) {
-            const double nx = s_obs[q].c, ny = s_obs[q].d;
-            const double h = -bl_dot2<FMA>(B.vx, B.vy, nx, ny);
-            if (h <= 0.0) continue;  // moving away from this wall (obstacles.py:117-118)
-            const double g = bl_sub(bl_dot2<FMA>(bl_sub(B.p0x, s_obs[q].a), bl_sub(B.p0y, s_obs[q].b), nx, ny), B.radius);
-            const double u = bl_div(g, h);
-            if (!(u < BL_T_EPS) && u < m) { m = u; qm = q; arg = h; }
-        }
+        for (int q = 2; q < O.n_obs; q++) wall_fold<FMA>(wall_at(O, q), q, B, m, qm, arg);
         B.ot = bl_add(t, m); B.oidx = qm; B.oarg = arg;
         return;
     }
-    bl_next_obstacle<FMA>(s_obs, n_obs, rsum2_obs, K, B.rc, B.p0x, B.p0y, B.vx, B.vy, B.radius, t, B.ot, B.oidx, B.oarg);
+    bl_next_obstacle<FMA>(O.s_obs, O.n_obs, O.rsum2_obs, O.K, B.rc, B.p0x, B.p0y, B.vx, B.vy, B.radius, t, B.ot, B.oidx,
+                          B.oarg);
+}
+template <bool FMA>
+__device__ __forceinline__ void next_obstacle_both(const Obstacles &O, double t, Ball &A, Ball &B) {
+    if (O.walls_only) {
+        double ma = BL_INF, mb = BL_INF, arga = 0.0, argb = 0.0;
+        int qa = -1, qb = -1;
+        if (O.n_obs > 0) wall_fold2<FMA>(O.w0, 0, A, B, ma, qa, arga, mb, qb, argb);
+        if (O.n_obs > 1) wall_fold2<FMA>(O.w1, 1, A, B, ma, qa, arga, mb, qb, argb);
+#pragma unroll 1
+        for (int q = 2; q < O.n_obs; q++) wall_fold2<FMA>(wall_at(O, q), q, A, B, ma, qa, arga, mb, qb, argb);
+        A.ot = bl_add(t, ma); A.oidx = qa; A.oarg = arga;
+        B.ot = bl_add(t, mb); B.oidx = qb; B.oarg = argb;
+        return;
+    }
+    next_obstacle_ball<FMA>(O, t, A);
+    next_obstacle_ball<FMA>(O, t, B);
 }
 
 // one obstacle collision of `me` at time t (simulation.py:504-554 with N <= 2); returns a bl_status
 template <bool FMA>
-__device__ __forceinline__ int obstacle_event(const bl_obstacle *s_obs, int n_obs, bool walls_only,
-                                              const double *rsum2_obs, int K, bool two, double rs01, double t, Ball &me,
+__device__ __forceinline__ int obstacle_event(const Obstacles &O, bool two, double rs01, double t, Ball &me,
                                               const Ball &other, double &T01, double *payload) {
     const double ax = bl_advance(me.p0x, me.vx, t, me.t0), ay = bl_advance(me.p0y, me.vy, t, me.t0);
     double wx = me.vx, wy = me.vy;
     const int oi = me.oidx;
     if (oi < 0) return BL_EASSERT;
-    int st = BL_OK;
-    if (walls_only) {  // InfiniteWall.resolve_collision, obstacles.py:135-144
-        wx = bl_add(me.vx, bl_mul(2.0, bl_mul(me.oarg, s_obs[oi].c)));
-        wy = bl_add(me.vy, bl_mul(2.0, bl_mul(me.oarg, s_obs[oi].d)));
+    if (O.walls_only) {  // InfiniteWall.resolve_collision, obstacles.py:135-144
+        const double nx = oi == 0 ? O.w0.nx : (oi == 1 ? O.w1.nx : O.s_obs[oi].c);
+        const double ny = oi == 0 ? O.w0.ny : (oi == 1 ? O.w1.ny : O.s_obs[oi].d);
+        wx = bl_add(me.vx, bl_mul(2.0, bl_mul(me.oarg, nx)));
+        wy = bl_add(me.vy, bl_mul(2.0, bl_mul(me.oarg, ny)));
     } else {
-        st = bl_obstacle_bounce<FMA>(s_obs[oi], ax, ay, me.vx, me.vy, me.oarg, wx, wy);
+        const int st = bl_obstacle_bounce<FMA>(O.s_obs[oi], ax, ay, me.vx, me.vy, me.oarg, wx, wy);
         if (st != BL_OK) return st;
     }
     if (payload) {
@@ -389,8 +444,8 @@ __device__ __forceinline__ int obstacle_event(const bl_obstacle *s_obs, int n_ob
         const double ox = bl_advance(other.p0x, other.vx, t, other.t0), oy = bl_advance(other.p0y, other.vy, t, other.t0);
         T01 = bl_add(t, bl_toi_ball_ball<FMA>(ax, ay, wx, wy, ox, oy, other.vx, other.vy, rs01));
     }
-    next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, rsum2_obs, K, t, me);
-    return st;
+    next_obstacle_ball<FMA>(O, t, me);
+    return BL_OK;
 }
 
 template <bool FMA, bool SINGLE>
@@ -405,11 +460,16 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
         if (s_obs[q].kind != BL_OBS_WALL) s_walls_only = 0;
     }
     __syncthreads();
-    const bool walls_only = s_walls_only != 0;
     const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= P.n_sys) return;
     const long long sb = sys * n;
     const bool two = n == 2;
+    Obstacles O;
+    O.s_obs = s_obs; O.rsum2_obs = P.rsum2_obs; O.n_obs = n_obs; O.K = K; O.walls_only = s_walls_only != 0;
+    O.w0.sx = O.w0.sy = O.w0.nx = O.w0.ny = 0.0;
+    O.w1 = O.w0;
+    if (O.walls_only && n_obs > 0) O.w0 = wall_at(O, 0);
+    if (O.walls_only && n_obs > 1) O.w1 = wall_at(O, 1);
 
     Ball b0, b1;
     b0.p0x = P.p0x[sb]; b0.p0y = P.p0y[sb]; b0.vx = P.vx[sb]; b0.vy = P.vy[sb]; b0.t0 = P.t0[sb];
@@ -443,24 +503,27 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
     }
 
     const bool want_log = SINGLE && P.log.cap > 0;
+    // the two limits, in registers: collisions this launch may handle (max_events and the log's capacity) and the
+    // last admissible time (finite: an impact time of +inf or NaN fails `t <= t_last` too)
+    long long limit = P.max_events >= 0 ? P.max_events : 0x7fffffffffffffffLL;
+    if (want_log && P.log.cap < limit) limit = P.log.cap;
+    double t_last = P.end_time < 1.7976931348623157e308 ? P.end_time : 1.7976931348623157e308;
+    asm volatile("" : "+l"(limit), "+d"(t_last));
     long long done = 0, n_bb = 0;
     int kind = KIND_BOTH;
     if (SINGLE) kind = P.first_kind == BL_BALL_BALL ? KIND_BB : (P.first_kind == BL_BALL_OBSTACLE ? KIND_BO : KIND_BOTH);
-    // why the loop ended: 0 time, 1 events, 2 log, 3 NaN time, 4 collision not resolvable (status in st)
+    // why the loop ended: 0 a limit (which one is sorted out below), 4 collision not resolvable (status in st)
     int why = 0, st = BL_OK, a = -1, b = -1;
     double t = now;
-    bool o1 = false;
+    bool o1 = false, take_bb = false;
     if (!(SINGLE && P.query_only)) {
         for (;;) {
             // next_ball_ball_collision / next_ball_obstacle_collision: first ball on ties, ball-ball wins a tie
             o1 = b1.ot < b0.ot;
             const double bo_t = o1 ? b1.ot : b0.ot;
-            const bool take_bb = kind == KIND_BB || (kind == KIND_BOTH && T01 < BL_INF && !(bo_t < T01));
+            take_bb = kind == KIND_BOTH ? !(bo_t < T01) : kind == KIND_BB;
             t = take_bb ? T01 : bo_t;
-            if (P.max_events >= 0 && done >= P.max_events) { why = 1; break; }
-            if (t != t) { why = 3; a = take_bb ? 0 : (int)o1; b = take_bb ? 1 : -1; break; }
-            if (!(t <= P.end_time) || !(t < BL_INF)) break;
-            if (want_log && done >= P.log.cap) { why = 2; break; }
+            if (done >= limit || !(t <= t_last)) break;
             double *payload = nullptr;
             if (want_log) {
                 P.log.t[done] = t;
@@ -485,19 +548,25 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
                 b0.p0x = ax; b0.p0y = ay; b0.vx = avx; b0.vy = avy; b0.t0 = t;
                 b1.p0x = bx; b1.p0y = by; b1.vx = bvx; b1.vy = bvy; b1.t0 = t;
                 T01 = BL_INF;  // :458
-                next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b0);
-                next_obstacle_ball<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b1);
+                next_obstacle_both<FMA>(O, t, b0, b1);
                 n_bb++;
             } else {
                 if (want_log) { P.log.i[done] = (int)o1; P.log.j[done] = -1 - (long long)(o1 ? b1.oidx : b0.oidx); }
-                st = o1 ? obstacle_event<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, two, rs01, t, b1, b0, T01, payload)
-                        : obstacle_event<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, two, rs01, t, b0, b1, T01, payload);
+                st = o1 ? obstacle_event<FMA>(O, two, rs01, t, b1, b0, T01, payload)
+                        : obstacle_event<FMA>(O, two, rs01, t, b0, b1, T01, payload);
                 if (st != BL_OK) { why = 4; a = (int)o1; b = -1; break; }
             }
             done++;
             now = t;
             kind = KIND_BOTH;  // only the first event's kind was forced
         }
+    }
+    // which limit ended the loop, in the order of the other kernels' stop rules: count, NaN, time, log
+    if (why == 0 && !(SINGLE && P.query_only)) {
+        if (P.max_events >= 0 && done >= P.max_events) why = 1;
+        else if (t != t) { why = 3; a = take_bb ? 0 : (int)o1; b = take_bb ? 1 : -1; }
+        else if (!(t <= t_last)) why = 0;
+        else why = 2;
     }
     o1 = b1.ot < b0.ot;
 
@@ -514,8 +583,8 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
     const int status = why == 3 ? (int)BL_ENAN : (why == 4 ? st : (int)BL_OK);
     if (SINGLE) {
         const bool some = T01 < BL_INF;
-        P.cover_t[0] = T01; P.cover_code[0] = some ? bl_pair_code(0, 1) : BL_CODE_NONE;
-        if (two) { P.cover_t[1] = T01; P.cover_code[1] = some ? bl_pair_code(0, 1) : BL_CODE_NONE; }
+        P.cover_t[0] = some ? T01 : BL_INF; P.cover_code[0] = some ? bl_pair_code(0, 1) : BL_CODE_NONE;
+        if (two) { P.cover_t[1] = some ? T01 : BL_INF; P.cover_code[1] = some ? bl_pair_code(0, 1) : BL_CODE_NONE; }
         bl_result *const res = P.result;
         double tnow = failed ? t : now;
         if (why == 0 && P.end_time < BL_INF) tnow = P.end_time;  // _move(end_time), :436
