@@ -391,10 +391,14 @@ __device__ __forceinline__ void next_obstacle_ball(const Obstacles &O, double t,
     if (O.walls_only) {
         double m = BL_INF, arg = 0.0;
         int qm = -1;
-        if (O.n_obs > 0) wall_fold<FMA>(O.w0, 0, B, m, qm, arg);
-        if (O.n_obs > 1) wall_fold<FMA>(O.w1, 1, B, m, qm, arg);
+        if (O.n_obs > 0) {
+            wall_fold<FMA>(O.w0, 0, B, m, qm, arg);
+            if (O.n_obs > 1) {
+                wall_fold<FMA>(O.w1, 1, B, m, qm, arg);
 #pragma unroll 1
-        for (int q = 2; q < O.n_obs; q++) wall_fold<FMA>(wall_at(O, q), q, B, m, qm, arg);
+                for (int q = 2; q < O.n_obs; q++) wall_fold<FMA>(wall_at(O, q), q, B, m, qm, arg);
+            }
+        }
         B.ot = bl_add(t, m); B.oidx = qm; B.oarg = arg;
         return;
     }
@@ -406,10 +410,14 @@ __device__ __forceinline__ void next_obstacle_both(const Obstacles &O, double t,
     if (O.walls_only) {
         double ma = BL_INF, mb = BL_INF, arga = 0.0, argb = 0.0;
         int qa = -1, qb = -1;
-        if (O.n_obs > 0) wall_fold2<FMA>(O.w0, 0, A, B, ma, qa, arga, mb, qb, argb);
-        if (O.n_obs > 1) wall_fold2<FMA>(O.w1, 1, A, B, ma, qa, arga, mb, qb, argb);
+        if (O.n_obs > 0) {
+            wall_fold2<FMA>(O.w0, 0, A, B, ma, qa, arga, mb, qb, argb);
+            if (O.n_obs > 1) {
+                wall_fold2<FMA>(O.w1, 1, A, B, ma, qa, arga, mb, qb, argb);
 #pragma unroll 1
-        for (int q = 2; q < O.n_obs; q++) wall_fold2<FMA>(wall_at(O, q), q, A, B, ma, qa, arga, mb, qb, argb);
+                for (int q = 2; q < O.n_obs; q++) wall_fold2<FMA>(wall_at(O, q), q, A, B, ma, qa, arga, mb, qb, argb);
+            }
+        }
         A.ot = bl_add(t, ma); A.oidx = qa; A.oarg = arga;
         B.ot = bl_add(t, mb); B.oidx = qb; B.oarg = argb;
         return;
@@ -448,7 +456,8 @@ __device__ __forceinline__ int obstacle_event(const Obstacles &O, bool two, doub
     return BL_OK;
 }
 
-template <bool FMA, bool SINGLE>
+// LOG: the launch writes the device event log (a compile-time flag: three fewer branches per collision otherwise)
+template <bool FMA, bool SINGLE, bool LOG>
 __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const __grid_constant__ SmallParams P) {
     __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
     __shared__ int s_walls_only;
@@ -463,9 +472,21 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
     const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= P.n_sys) return;
     const long long sb = sys * n;
-    const bool two = n == 2;
+    bool two = n == 2;
+    {
+        int tw = two ? 1 : 0;
+        asm volatile("" : "+r"(tw));
+        two = tw != 0;
+    }
     Obstacles O;
     O.s_obs = s_obs; O.rsum2_obs = P.rsum2_obs; O.n_obs = n_obs; O.K = K; O.walls_only = s_walls_only != 0;
+    {
+        // loop-invariant flags as opaque register values: left to itself the compiler re-derives them from the
+        // constant bank inside the loop (load + compare + branch, ~20 cycles of latency each time, several per collision)
+        int wo = O.walls_only ? 1 : 0, no = n_obs;
+        asm volatile("" : "+r"(wo), "+r"(no));
+        O.walls_only = wo != 0; O.n_obs = no;
+    }
     O.w0.sx = O.w0.sy = O.w0.nx = O.w0.ny = 0.0;
     O.w1 = O.w0;
     if (O.walls_only && n_obs > 0) O.w0 = wall_at(O, 0);
@@ -482,6 +503,8 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
         b1.mass = P.mass[1]; b1.radius = P.radius[1]; b1.rc = P.rclass[1];
     }
     const double rs01 = P.rsum2[(size_t)b0.rc * K + b1.rc];
+    double m1r = b0.mass, m2r = b1.mass;  // simulation.py:579-582, the same for every collision of the pair
+    bl_remap_masses(m1r, m2r);
     double T01 = BL_INF;
     double now = SINGLE ? P.time : P.sys_time[sys];
     double *const tab = P.toi + sys * P.toi_sys_stride;
@@ -502,7 +525,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
         }
     }
 
-    const bool want_log = SINGLE && P.log.cap > 0;
+    constexpr bool want_log = LOG;
     // the two limits, in registers: collisions this launch may handle (max_events and the log's capacity) and the
     // last admissible time (finite: an impact time of +inf or NaN fails `t <= t_last` too)
     long long limit = P.max_events >= 0 ? P.max_events : 0x7fffffffffffffffLL;
@@ -533,8 +556,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const
                 // bounce_ball_ball, simulation.py:440-502 with N = 2: nothing else to re-solve
                 const double ax = bl_advance(b0.p0x, b0.vx, t, b0.t0), ay = bl_advance(b0.p0y, b0.vy, t, b0.t0);
                 const double bx = bl_advance(b1.p0x, b1.vx, t, b1.t0), by = bl_advance(b1.p0y, b1.vy, t, b1.t0);
-                double m1 = b0.mass, m2 = b1.mass;
-                bl_remap_masses(m1, m2);
+                const double m1 = m1r, m2 = m2r;
                 double avx = b0.vx, avy = b0.vy, bvx = b1.vx, bvy = b1.vy;
                 st = elastic_pair<FMA>(ax, ay, b0.vx, b0.vy, m1, bx, by, b1.vx, b1.vy, m2, avx, avy, bvx, bvy);
                 if (st != BL_OK) { why = 4; a = 0; b = 1; break; }
@@ -613,7 +635,10 @@ template <bool FMA, bool SINGLE>
 cudaError_t launch_n(const SmallParams &P, cudaStream_t st) {
     const unsigned grid = SINGLE ? 1u : (unsigned)((P.n_sys + 127) / 128);
     const unsigned block = SINGLE ? 32u : 128u;
-    if (P.n <= 2) bl_evolve_pair_kernel<FMA, SINGLE><<<grid, block, 0, st>>>(P);
+    if (P.n <= 2) {
+        if (SINGLE && P.log.cap > 0) bl_evolve_pair_kernel<FMA, SINGLE, SINGLE><<<grid, block, 0, st>>>(P);
+        else bl_evolve_pair_kernel<FMA, SINGLE, false><<<grid, block, 0, st>>>(P);
+    }
     else bl_evolve_tiny_kernel<FMA, 4, SINGLE><<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
 }
