@@ -663,6 +663,9 @@ int orc_ensemble_run2(int dot_fma, const orc_obstacle *obs, int nobs, long long 
     return ORC_OK;
 }
 
+/* libm's fma, for the dot-mode probe of oracle.py */
+double orc_fma(double a, double b, double c) { return fma(a, b, c); }
+
 int orc_ensemble_run(int dot_fma, const orc_obstacle *obs, int nobs, long long n_sys, double radius,
                      double *state, double *t_out, long long n_coll, long long *done, int32_t *hits) {
     return orc_ensemble_run2(dot_fma, obs, nobs, n_sys, radius, state, t_out, n_coll, done, hits, NULL);

@@ -98,6 +98,24 @@ def lib():
     return _LIB
 
 
+def probe_dot_fma():
+    """Which formula does THIS host's numpy use for a 2-vector dot?  True: fma(a1, b1, fl(a0*b0)) (OpenBLAS on FMA
+    hosts), False: fl(fl(a0*b0) + fl(a1*b1)).  The oracle restates whichever the reference
+    would compute on this machine; bench.py's CPU legs call this instead of importing the product package."""
+    L = lib()
+    L.orc_fma.restype = ctypes.c_double
+    L.orc_fma.argtypes = [ctypes.c_double] * 3
+    rng = np.random.default_rng(20240229)
+    a, b = rng.standard_normal((2048, 2)), rng.standard_normal((2048, 2))
+    fused = plain = True
+    for x, y in zip(a, b):
+        d = float(x.dot(y))
+        x0, x1, y0, y1 = float(x[0]), float(x[1]), float(y[0]), float(y[1])
+        fused = fused and d == L.orc_fma(x1, y1, x0 * y0)
+        plain = plain and d == x0 * y0 + x1 * y1
+    return fused if fused != plain else True
+
+
 def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 

@@ -33,6 +33,76 @@ def shard_bounds(n_total, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+_pinned_cache = {}
+
+
+def _pinned(name, shape, dtype):
+    """page-locked host buffer, allocated once per (name, shape, dtype) and reused by later calls"""
+    import torch
+    key = (name, tuple(shape), dtype)
+    buf = _pinned_cache.get(key)
+    if buf is None:
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _pinned_cache[key] = buf
+    return buf
+
+
+def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, device=None, dot_fma=None, chunks=4,
+                  count_hits=False):
+    """One-ball ensembles, host arrays in -> host arrays out, with the copies hidden behind the kernel.
+
+    The systems are split into ``chunks`` contiguous blocks; block c goes host -> device, runs and comes back on its own
+    CUDA stream, so the copy engines work on one block while the SMs run the collision loop of another (the kernel is
+    bound by the FP64 pipe, the copies by PCIe).  Results are what ``BilliardEnsemble(...).run(n_collisions)`` gives
+    (systems are independent: the partition does not matter).  ``pos`` / ``vel`` should be pinned torch CPU tensors
+    (or numpy arrays: they are staged through a pinned buffer first).  Returns a dict of numpy arrays ``time`` (S,),
+    ``position`` (S, 2) (of the last collision), ``velocity`` (S, 2), ``counts`` (S,) and ``stats`` -- views of pinned
+    buffers that the next call overwrites.
+    """
+    import torch
+    pos_t, vel_t = _as_f64_tensor(pos).reshape(-1, 2), _as_f64_tensor(vel).reshape(-1, 2)
+    S = pos_t.shape[0]
+    if not pos_t.is_pinned():
+        pos_t = _pinned("in_pos", pos_t.shape, torch.float64).copy_(pos_t)
+    if not vel_t.is_pinned():
+        vel_t = _pinned("in_vel", vel_t.shape, torch.float64).copy_(vel_t)
+    h = _lib.get_handle(device, dot_fma)
+    dev = h.torch_device
+    out_t = _pinned("out_t", (S,), torch.float64)
+    out_p = _pinned("out_p", (S, 2), torch.float64)
+    out_v = _pinned("out_v", (S, 2), torch.float64)
+    out_c = _pinned("out_c", (S,), torch.int64)
+    chunks = max(1, min(int(chunks), S))
+    streams = _pinned_cache.setdefault(("streams", dev.index, chunks), [torch.cuda.Stream(dev) for _ in range(chunks)])
+    parts = []
+    start = torch.cuda.current_stream(dev)
+    for c in range(chunks):
+        lo, hi = shard_bounds(S, chunks, c)
+        st = streams[c]
+        st.wait_stream(start)
+        with torch.cuda.stream(st):
+            ens = BilliardEnsemble(obstacles, pos_t[lo:hi], vel_t[lo:hi], radius=radius, device=dev.index,
+                                   dot_fma=h.dot_fma, count_hits=count_hits)
+            ens.run(n_collisions, end_time, sync=False)
+            out_t[lo:hi].copy_(ens._time, non_blocking=True)
+            out_p[lo:hi].copy_(ens._state[0:2].T, non_blocking=True)
+            out_v[lo:hi].copy_(ens._state[2:4].T, non_blocking=True)
+            out_c[lo:hi].copy_(ens._counts, non_blocking=True)
+            parts.append(ens)
+    for st in streams:
+        start.wait_stream(st)  # the caller's stream continues after every block is back
+    total = torch.stack([p.stats() for p in parts]).sum(dim=0)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    total = total.cpu()  # synchronises the current stream, which waited for every chunk
+    bad = sum(int((p._status != 0).sum().item()) for p in parts)
+    if bad:
+        raise ValueError(f"{bad} systems hit a separating/degenerate collision (status != 0)")
+    return {"time": out_t.numpy(), "position": out_p.numpy(), "velocity": out_v.numpy(), "counts": out_c.numpy(),
+            "stats": total.numpy()}
+
+
 def _as_f64_tensor(x):
     import torch
     return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
@@ -296,3 +366,6 @@ class BilliardEnsemble:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM)
         return out.cpu().numpy()
+
+
+BilliardEnsemble.run_from_host = staticmethod(run_from_host)

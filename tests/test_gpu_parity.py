@@ -679,6 +679,55 @@ def test_full_size_ideal_gas_two_schedules(billiards):
     assert gap.min() >= 2.0 * r - 1e-9, "overlapping balls"
 
 
+def test_full_size_dense_gas_two_schedules(billiards):
+    """Config D at its full size (BASELINE.json: N = 16384 at packing fraction 0.5, 10^7 collisions) -- what bench.py
+    times.  Two decompositions of the same work must agree bit for bit: the default schedule (~30 collisions per
+    grid-wide round, launches of 10^6 collisions) against 9 keys per round in launches of 777 777 -- digest of the whole
+    event log, end state, reference-shaped row minima -- plus what the physics conserves on the state that is left."""
+    from billiards import _lib
+    import hashlib
+    import torch
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.dense_gas(128)
+    n_events = 10**7
+    runs = []
+    for target, chunk in ((0, 10**6), (9, 777777)):
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            sha = hashlib.sha256()
+            done, last_t, monotone = [0, 0], -INF, True
+            while sum(done) < n_events:
+                k = min(chunk, n_events - sum(done))
+                counts, (t, i, j) = bld.evolve_events(k, log_capacity=k)
+                assert sum(counts) == k == len(t)
+                done[0] += counts[0]
+                done[1] += counts[1]
+                monotone = monotone and bool((np.diff(t) >= -1e-10).all()) and t[0] >= last_t - 1e-10
+                last_t = float(t[-1])
+                sha.update(t.tobytes() + i.tobytes() + j.tobytes())
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        assert monotone
+        runs.append((tuple(done), sha.hexdigest(), bld.balls_velocity.copy(), bld.balls_position.copy(),
+                     bld._balls_toi.copy(), bld.time, bld._obstacles_toi.copy()))
+    a, b = runs
+    assert a[0] == b[0] and a[1] == b[1] and a[5] == b[5]
+    assert_bits_equal(a[2], b[2], "velocities")
+    assert_bits_equal(a[3], b[3], "positions")
+    assert_bits_equal(a[4], b[4], "_balls_toi")
+    assert_bits_equal(a[6], b[6], "_obstacles_toi")
+    v, p, r = a[2], a[3], float(cfg.radius[0])
+    assert abs(float((v * v).sum()) / cfg.n - 1.0) < 1e-9       # unit speeds, equal masses: sum |v|^2 is conserved
+    assert p.min() >= r - 1e-9 and p.max() <= 128.0 - r + 1e-9
+    pd = torch.from_numpy(p).cuda()
+    for lo in range(0, cfg.n, 2048):
+        d = torch.cdist(pd[lo:lo + 2048], pd, compute_mode="donot_use_mm_for_euclid_dist")
+        d[torch.arange(d.shape[0]), torch.arange(lo, lo + d.shape[0])] = INF
+        assert float(d.min().item()) >= 2.0 * r - 1e-9, "overlapping balls"
+
+
 def test_full_size_sinai_ensemble_is_partition_invariant(billiards):
     """Config S at its full size (2^20 systems x 10^4 collisions): one launch over all systems == two contiguous
     shards (what two ranks would run) == the same shard in two launches of 5000; speeds stay 1, every ball stays
