@@ -356,7 +356,8 @@ int bl_set_small_kernel(bl_handle *h, int enable) {
 
 int bl_set_ensemble_generic(bl_handle *h, int enable) {
     if (!h) return BL_EINVAL;
-    h->ensemble_generic = enable ? 1 : 0;
+    h->ensemble_generic = enable == 1 ? 1 : 0;
+    h->ensemble_no_box = enable == 2 ? 1 : 0;
     return BL_OK;
 }
 

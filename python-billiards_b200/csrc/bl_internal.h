@@ -34,6 +34,7 @@ struct bl_handle {
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
     int small_kernel_off;     // bl_set_small_kernel(h, 0): systems of <= 32 balls also take the grid-wide event kernel
     int small_force_lanes;    // bl_set_small_kernel(h, 2): systems of <= 4 balls take the lane-group kernel, not the one-thread kernel
+    int ensemble_no_box;      // bl_set_ensemble_generic(h, 2): shaped kernel, but without the axis-aligned-box shortcut
     int ensemble_generic;     // BL_ENSEMBLE_GENERIC=1: always use the generic (list in shared memory) ensemble kernel
     char err[512];
 };

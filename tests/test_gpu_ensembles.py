@@ -52,7 +52,7 @@ def _fuzz_case(rng, nw, nd, case):
     """obstacle list (user terms) + initial conditions for one randomised one-ball ensemble"""
     scale = 10.0 ** rng.uniform(-6, 6)
     shift = rng.uniform(-3, 3, 2) * scale * (case % 3 != 0)
-    axis_aligned = case % 4 == 0
+    axis_aligned = case % 4 == 0 or (nw == 4 and case % 2 == 1)  # the box shortcut of the shaped kernel
     if axis_aligned:
         verts = np.asarray([(-1.0, -1.0), (1.0, -1.0), (1.0, 1.0), (-1.0, 1.0)]) * rng.uniform(0.8, 1.3)
     else:
@@ -101,6 +101,9 @@ def _fuzz_case(rng, nw, nd, case):
         theta = np.where(tang, np.arctan2(dc[:, 1], dc[:, 0]) + off, theta)
     speed = 10.0 ** rng.uniform(-2, 2, n_sys)
     vel = np.stack([np.cos(theta), np.sin(theta)], axis=1) * speed[:, None] * scale
+    # motion exactly along an axis: one velocity component is a zero of either sign
+    for q in range(3, 203, 5):
+        vel[q, q % 2] = 0.0 if q % 3 else -0.0
     pos = pos * scale + shift
     # balls that start in contact with a wall: exactly at distance `radius` along its normal (gap = 0 up to rounding)
     if nw:
@@ -127,7 +130,7 @@ def test_shaped_ensemble_kernel_on_random_geometries(billiards, oracle, nw, nd):
         obstacles, pos, vel, radius = _fuzz_case(rng, nw, nd, case)
         obs = workloads.make_obstacles(billiards, obstacles)
         got = {}
-        for name, generic in (("shaped", 0), ("generic", 1)):
+        for name, generic in (("shaped", 0), ("generic", 1), ("shaped_no_box", 2)):
             h.check(h.lib.bl_set_ensemble_generic(h.h, generic))
             try:
                 ens = billiards.BilliardEnsemble(obs, pos, vel, radius=radius, dot_fma=fma, count_hits=True)
@@ -139,7 +142,7 @@ def test_shaped_ensemble_kernel_on_random_geometries(billiards, oracle, nw, nd):
         want = oracle.ensemble_run(workloads.oracle_obstacles(obstacles), pos, vel, n_coll, radius=radius, dot_fma=fma,
                                    count_hits=True, per_system_status=True)
         ref = (want["t"], want["v"], want["p0"], want["done"], want["hits"], want["status"])
-        for name in ("generic", "shaped"):
+        for name in ("generic", "shaped_no_box", "shaped"):
             what = f"<{nw},{nd}> case {case} {name}"
             for q, label in enumerate(("time", "velocity", "position")):
                 assert_bits_equal(got[name][q], ref[q], f"{what}: {label}")
@@ -147,8 +150,9 @@ def test_shaped_ensemble_kernel_on_random_geometries(billiards, oracle, nw, nd):
             assert got[name][4].tolist() == ref[4].tolist(), what
             assert got[name][5].tolist() == ref[5].tolist(), what
         total += int(want["done"].sum())
-    # closed shapes bounce for ever; open ones (fewer than three walls) let most balls escape after a few hits
-    assert total == 24 * 1500 * n_coll if nw >= 3 else total > 5000
+    # closed shapes bounce for ever (but for a few axis-parallel shots out of an open box); open ones (fewer than three
+    # walls) let most balls escape after a few hits
+    assert total > 0.97 * 24 * 1500 * n_coll if nw >= 3 else total > 5000
 
 
 def test_shared_reciprocal_division_is_ieee(billiards):
