@@ -71,7 +71,7 @@ __device__ __forceinline__ void next_obstacle_pair(const bl_obstacle *s_obs, int
 }
 
 template <bool FMA, int N, bool SINGLE>
-__global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_tiny_kernel(const __grid_constant__ SmallParams P) {
+__global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(const __grid_constant__ SmallParams P) {
     __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
     __shared__ int s_walls_only;
     const int n = P.n, K = P.K, n_obs = P.n_obs;
@@ -458,7 +458,7 @@ __device__ __forceinline__ int obstacle_event(const Obstacles &O, bool two, doub
 
 // LOG: the launch writes the device event log (a compile-time flag: three fewer branches per collision otherwise)
 template <bool FMA, bool SINGLE, bool LOG>
-__global__ void __launch_bounds__(SINGLE ? 32 : 128) bl_evolve_pair_kernel(const __grid_constant__ SmallParams P) {
+__global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_pair_kernel(const __grid_constant__ SmallParams P) {
     __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
     __shared__ int s_walls_only;
     const int n = P.n, K = P.K, n_obs = P.n_obs;
