@@ -45,6 +45,32 @@ __device__ __forceinline__ void group_min(unsigned gmask, double &t, uint64_t &c
     }
 }
 
+// minimum of a table row of W entries (entries past the last ball hold +inf) and its first index: chunks of eight
+// loads reduced by a compare tree -- a dependent chain of 3 + W/8 compares instead of W
+template <int W>
+__device__ __forceinline__ void row_min(const double *Trow, double &best, int &bj) {
+    best = BL_INF; bj = -1;
+    constexpr int C = W < 8 ? W : 8;
+#pragma unroll
+    for (int base = 0; base < W; base += C) {
+        double v[C];
+        int ix[C];
+#pragma unroll
+        for (int q = 0; q < C; q++) { v[q] = Trow[base + q]; ix[q] = base + q; }
+#pragma unroll
+        for (int step = 1; step < C; step <<= 1)
+#pragma unroll
+            for (int q = 0; q + step < C; q += 2 * step) {
+                const bool lt = v[q + step] < v[q];  // strict: the lower index survives a tie (numpy's argmin)
+                v[q] = lt ? v[q + step] : v[q];
+                ix[q] = lt ? ix[q + step] : ix[q];
+            }
+        const bool lt = v[0] < best;
+        best = lt ? v[0] : best;
+        bj = lt ? ix[0] : bj;
+    }
+}
+
 template <bool FMA, int W, bool SINGLE>
 __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
     bl_evolve_small_kernel(const __grid_constant__ SmallParams P) {
@@ -98,14 +124,21 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
             ot = P.obs_t[sb + li]; oarg = P.obs_arg[sb + li]; oidx = P.obs_idx[sb + li];
             const double *src = P.toi + sys * P.toi_sys_stride + (size_t)li * P.toi_pitch;
             for (int j = 0; j < n; j++) Trow[j] = src[j];
+            for (int j = n; j < W; j++) Trow[j] = BL_INF;  // row_min scans all W entries
             Trow[li] = BL_INF;
         } else {
-            for (int j = 0; j < n; j++) Trow[j] = BL_INF;
+            for (int j = 0; j < W; j++) Trow[j] = BL_INF;
         }
     }
     __syncwarp(gmask);
 
     const bool want_log = SINGLE && P.log.cap > 0;
+    // the limits as opaque register values (re-reading kernel parameters from the constant bank inside the loop costs a
+    // load, a compare and a branch each time): collisions this launch may handle, room in the log, last admissible time
+    long long max_ev = P.max_events >= 0 ? P.max_events : 0x7fffffffffffffffLL;
+    long long log_cap = want_log ? P.log.cap : 0x7fffffffffffffffLL;
+    double end_t = P.end_time;
+    asm volatile("" : "+l"(max_ev), "+l"(log_cap), "+d"(end_t));
     bl_result *const res = P.result;
     long long done = 0, n_bb = 0;
     int kindmask = KIND_BOTH, final_stage = 0;
@@ -121,13 +154,8 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
         uint64_t kc = BL_CODE_END;
         if (own) {
             if (kindmask != KIND_BO) {
-                int bj = -1;
-                for (int j = 0; j < n; j++) {
-                    const double v = Trow[j];
-                    const bool lt = v < kt;
-                    kt = lt ? v : kt;
-                    bj = lt ? j : bj;
-                }
+                int bj;
+                row_min<W>(Trow, kt, bj);
                 kc = bj >= 0 ? bl_pair_code(li, bj) : BL_CODE_NONE;
             }
             if (kindmask != KIND_BB) {
@@ -142,10 +170,10 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
         // ---- stop rules ----
         int stop_kind = -1, st_status = BL_OK;
         if (SINGLE && final_stage != 0) stop_kind = BL_STOP_TIME;
-        else if (P.max_events >= 0 && done >= P.max_events) stop_kind = BL_STOP_EVENTS;
+        else if (done >= max_ev) stop_kind = BL_STOP_EVENTS;
         else if (t != t) { stop_kind = BL_STOP_ERROR; st_status = BL_ENAN; }
-        else if (!(t <= P.end_time) || !(t < BL_INF) || cd == BL_CODE_NONE || cd == BL_CODE_END) stop_kind = BL_STOP_TIME;
-        else if (want_log && done >= P.log.cap) stop_kind = BL_STOP_LOG;
+        else if (!(t <= end_t) || !(t < BL_INF) || cd == BL_CODE_NONE || cd == BL_CODE_END) stop_kind = BL_STOP_TIME;
+        else if (done >= log_cap) stop_kind = BL_STOP_LOG;
 
         int a = -1, b = -1;
         if (cd != BL_CODE_NONE && cd != BL_CODE_END) {
@@ -235,21 +263,77 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
         if (own && li != a && li != b) {
             // ---- every other ball re-solves its pair with the colliding ball(s); simulation.py:461-471, :522-526 ----
             const double px = bl_advance(p0x, vx, t, t0), py = bl_advance(p0y, vy, t, t0);
+            // both quadratics of physics.py:33-54 side by side (two independent chains), then the square root and the
+            // division only for a pair that gets past the two early exits
             const double rsa = K == 1 ? rs_one : rs_row[rca];
-            const double va = bl_add(t, bl_toi_ball_ball<FMA>(ax, ay, avx, avy, px, py, vx, vy, rsa));
-            Trow[a] = va; Tg[a * RP + li] = va;
+            const double dax = bl_sub(px, ax), day = bl_sub(py, ay), dvax = bl_sub(vx, avx), dvay = bl_sub(vy, avy);
+            const double qb_a = bl_dot2<FMA>(dax, day, dvax, dvay);
+            const double qc_a = bl_sub(bl_dot2<FMA>(dax, day, dax, day), rsa);
+            const double qd_a = bl_sub(bl_mul(qb_a, qb_a), bl_mul(bl_dot2<FMA>(dvax, dvay, dvax, dvay), qc_a));
+            double va = BL_INF, vb = BL_INF;
+            double qb_b = 0.0, qc_b = 0.0, qd_b = 0.0;
             if (b >= 0) {
                 const double rsb = K == 1 ? rs_one : rs_row[rcb];
-                const double vb = bl_add(t, bl_toi_ball_ball<FMA>(bx, by, bvx, bvy, px, py, vx, vy, rsb));
+                const double dbx = bl_sub(px, bx), dby = bl_sub(py, by), dvbx = bl_sub(vx, bvx), dvby = bl_sub(vy, bvy);
+                qb_b = bl_dot2<FMA>(dbx, dby, dvbx, dvby);
+                qc_b = bl_sub(bl_dot2<FMA>(dbx, dby, dbx, dby), rsb);
+                qd_b = bl_sub(bl_mul(qb_b, qb_b), bl_mul(bl_dot2<FMA>(dvbx, dvby, dvbx, dvby), qc_b));
+            }
+            if (!(qb_a >= 0.0) && !(qd_a <= 0.0)) {
+                const double t1 = bl_div(qc_a, bl_add(-qb_a, bl_sqrt(qd_a)));
+                va = t1 >= BL_T_EPS ? t1 : BL_INF;
+            }
+            va = bl_add(t, va);
+            Trow[a] = va; Tg[a * RP + li] = va;
+            if (b >= 0) {
+                if (!(qb_b >= 0.0) && !(qd_b <= 0.0)) {
+                    const double t1 = bl_div(qc_b, bl_add(-qb_b, bl_sqrt(qd_b)));
+                    vb = t1 >= BL_T_EPS ? t1 : BL_INF;
+                }
+                vb = bl_add(t, vb);
                 Trow[b] = vb; Tg[b * RP + li] = vb;
             }
         } else if (own) {
-            // ---- the colliding balls: new state of record, pair entry = inf (:458), next obstacle (:490-495, :545-547) ----
+            // ---- the colliding balls: new state of record, pair entry = inf (:458) ----
             if (li == a) { p0x = ax; p0y = ay; vx = avx; vy = avy; }
             else { p0x = bx; p0y = by; vx = bvx; vy = bvy; }
             t0 = t;
             if (b >= 0) Trow[li == a ? b : a] = BL_INF;
-            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc, p0x, p0y, vx, vy, radius, t, ot, oidx, oarg);
+        }
+        // ---- next obstacle of the colliding balls (:490-495, :545-547), spread over the lanes of the group: lane l
+        // takes the obstacles (l >> 1), (l >> 1) + W/2, ... for ball a (even lanes) or b (odd lanes); the partial minima
+        // are combined by a butterfly over the lanes of equal parity -- smaller time, then smaller list index, which is
+        // the reference's strict < in list order ----
+        {
+            const int which = li & 1;
+            const int tball = which ? b : a;
+            const double tx = which ? bx : ax, ty = which ? by : ay, tvx = which ? bvx : avx, tvy = which ? bvy : avy;
+            const int src = tball >= 0 ? tball : 0;
+            const double tradius = __shfl_sync(gmask, radius, src, W);
+            const int trc = which ? rcb : rca;
+            double omin = BL_INF, oam = 0.0;
+            int oq = -1;
+            if (tball >= 0) {
+                for (int q = li >> 1; q < n_obs; q += (W > 2 ? W / 2 : 1)) {
+                    double arg;
+                    const double rs = s_obs[q].kind != BL_OBS_WALL ? P.rsum2_obs[(size_t)q * K + trc] : 0.0;
+                    const double tq = bl_obstacle_toi<FMA>(s_obs[q], tx, ty, tvx, tvy, tradius, rs, arg);
+                    if (tq < omin) { omin = tq; oq = q; oam = arg; }
+                }
+            }
+#pragma unroll
+            for (int o = 2; o < W; o <<= 1) {
+                const double t2 = __shfl_xor_sync(gmask, omin, o, W), a2 = __shfl_xor_sync(gmask, oam, o, W);
+                const int q2 = __shfl_xor_sync(gmask, oq, o, W);
+                const bool take = t2 < omin || (t2 == omin && q2 >= 0 && (oq < 0 || q2 < oq));
+                omin = take ? t2 : omin; oam = take ? a2 : oam; oq = take ? q2 : oq;
+            }
+            const double t_a = __shfl_sync(gmask, omin, 0, W), g_a = __shfl_sync(gmask, oam, 0, W);
+            const int q_a = __shfl_sync(gmask, oq, 0, W);
+            const double t_b = __shfl_sync(gmask, omin, 1, W), g_b = __shfl_sync(gmask, oam, 1, W);
+            const int q_b = __shfl_sync(gmask, oq, 1, W);
+            if (li == a) { ot = bl_add(t, t_a); oidx = q_a; oarg = g_a; }
+            if (li == b) { ot = bl_add(t, t_b); oidx = q_b; oarg = g_b; }
         }
         __syncwarp(gmask);
         done++;

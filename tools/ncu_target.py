@@ -22,6 +22,22 @@ if what == "gas":
     bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
     print("warm-up", bld.evolve_events(events))
     print("measured", bld.evolve_events(events), "kernel ms", _lib.get_handle(0, fma).last_kernel_ms())
+elif what == "pool_ensemble":
+    import numpy as np
+    S = int(sys.argv[2])
+    cfg = workloads.pool()
+    rng = np.random.default_rng(2000)
+    pos = np.ascontiguousarray(np.broadcast_to(cfg.pos[None], (S,) + cfg.pos.shape))
+    vel = np.ascontiguousarray(np.broadcast_to(cfg.vel[None], (S,) + cfg.vel.shape))
+    speed = cfg.vel[15, 0] * rng.uniform(0.8, 1.2, S)
+    ang = rng.uniform(-0.02, 0.02, S)
+    vel[:, 15, 0] = speed * np.cos(ang)
+    vel[:, 15, 1] = speed * np.sin(ang)
+    obs = workloads.make_obstacles(billiards, cfg.obstacles)
+    for _ in range(2):
+        ens = billiards.BilliardEnsemble(obs, pos, vel, radius=cfg.radius, mass=cfg.mass, dot_fma=fma)
+        ens.run(-1, end_time=100.0)
+    print("pool ensemble", int(ens.counts.sum()), "collisions, kernel ms", _lib.get_handle(0, fma).last_kernel_ms())
 elif what == "galperin":
     b = workloads.galperin().build(billiards, dot_fma=fma)
     print(b.evolve(16))
