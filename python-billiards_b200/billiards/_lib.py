@@ -80,6 +80,7 @@ SIGNATURES = {
     "bl_evolve": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int,
                                  ctypes.POINTER(BlLog), ctypes.POINTER(BlResult), c_void]),
     "bl_next": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.POINTER(BlResult), c_void]),
+    "bl_snapshot": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void, c_void]),
     "bl_positions": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void]),
     "bl_toi_ball_ball": (ctypes.c_int, [_H, c_void, c_void, ctypes.c_double, c_void, ctypes.c_int64, c_void]),
     "bl_elastic_collision": (ctypes.c_int, [_H, c_void, c_void, c_void, ctypes.c_int64, c_void]),

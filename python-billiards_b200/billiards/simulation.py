@@ -229,17 +229,21 @@ class Billiard:
         if self._host_valid:
             return
         self._flush()
-        h, n, d = self._h(), self._n, self._dev
+        h, n = self._h(), self._n
         if n:
-            pos = torch.empty((n, 2), dtype=torch.float64, device=h.torch_device)
+            # one launch + one device -> pinned-host copy (bl_snapshot); the mirrors are fresh arrays, like the
+            # reference's, so that references a caller kept to earlier arrays stay what they were
+            snap = getattr(self, "_snap", None)
+            if snap is None or snap[0] < n:
+                cap = max(n, 2 * (snap[0] if snap else 0))
+                snap = (cap, torch.empty(8 * cap, dtype=torch.float64, device=h.torch_device),
+                        torch.empty(8 * cap, dtype=torch.float64, pin_memory=True))
+                self._snap = snap
             s = self._system()
-            h.check(h.lib.bl_positions(h.h, ctypes.byref(s), float(self._time), _lib.ptr(pos), h.stream()))
-            packed = torch.stack([pos[:, 0], pos[:, 1], d["vx"][:n], d["vy"][:n], d["p0x"][:n], d["p0y"][:n],
-                                  d["t0"][:n]], dim=1).cpu().numpy()
-            self._pos = np.ascontiguousarray(packed[:, 0:2])
-            self._vel = np.ascontiguousarray(packed[:, 2:4])
-            self._p0 = np.ascontiguousarray(packed[:, 4:6])
-            self._t0 = np.ascontiguousarray(np.repeat(packed[:, 6:7], 2, axis=1))
+            h.check(h.lib.bl_snapshot(h.h, ctypes.byref(s), float(self._time), _lib.ptr(snap[1]),
+                                      ctypes.c_void_p(snap[2].data_ptr()), h.stream()))
+            block = snap[2].numpy()[:8 * n].reshape(4, n, 2).copy()
+            self._pos, self._vel, self._p0, self._t0 = block[0], block[1], block[2], block[3]
         self._host_valid = True
 
     # ------------------------------------------------------------------------------------------------

@@ -227,6 +227,19 @@ int bl_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, v
     return bl_launch_positions(h, s, time, d_pos, as_stream(stream));
 }
 
+int bl_snapshot(bl_handle *h, const bl_system *s, double time, double *d_out, double *host_out, void *stream) {
+    bl_entry_guard g(h);
+    int rc = check_system(h, s);
+    if (rc) return rc;
+    if (!d_out) return BL_EINVAL;
+    cudaStream_t st = as_stream(stream);
+    rc = bl_launch_snapshot(h, s, time, d_out, st);
+    if (rc || !host_out || s->n == 0) return rc;
+    cudaError_t e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * 8 * (size_t)s->n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return bl_check_cuda(h, e, "bl_snapshot copy");
+}
+
 int bl_toi_ball_ball(bl_handle *h, const double *d_in, const double *d_rsum2, double t_eps, double *d_out, int64_t m,
                      void *stream) {
     bl_entry_guard g(h);

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(co
         int a = take_bb ? bb_lo : bo_k, b = take_bb ? bb_hi : -1;
         // Opaque to the optimiser on purpose.  nvcc 12.9 folded pick(x, b) to x[0] in the <N = 2, ensemble> instance of
         // this kernel (the PTX used ball 0 for both partners of a ball-ball collision: mass, position and velocity;
-        // seen on the GPU as BL_EDIVZERO in tests/test_gpu_ensembles.py::test_multi_ball_ensemble_against_oracle[2-1]).
+        // seen on the GPU as BL_EDIVZERO in the multi-ball ensemble parity test of tests/test_gpu_ensembles.py, case [2-1]).
         // With the indices hidden behind an empty asm every instance selects by the run-time value.  (Systems of one
         // or two balls have since moved to bl_evolve_pair_kernel below; the guard stays.)
         asm volatile("" : "+r"(a), "+r"(b));

@@ -140,6 +140,20 @@ __global__ void __launch_bounds__(256) bl_positions_kernel(const bl_system S, co
     pos[2 * k + 1] = bl_advance(S.p0y[k], S.vy[k], time, t0);
 }
 
+// everything the host mirrors of a Billiard in one pass: out = [4][n][2] = balls_position (at `time`), balls_velocity,
+// balls_initial_position, balls_initial_time (both columns) -- one launch and one copy per frame of an animation loop
+__global__ void __launch_bounds__(256) bl_snapshot_kernel(const bl_system S, const double time, double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S.n;
+    if (k >= n) return;
+    const double t0 = S.t0[k], p0x = S.p0x[k], p0y = S.p0y[k], vx = S.vx[k], vy = S.vy[k];
+    double2 *o = reinterpret_cast<double2 *>(out);
+    o[k] = make_double2(bl_advance(p0x, vx, time, t0), bl_advance(p0y, vy, time, t0));
+    o[n + k] = make_double2(vx, vy);
+    o[2 * n + k] = make_double2(p0x, p0y);
+    o[3 * n + k] = make_double2(t0, t0);
+}
+
 // recompute_toi's edit detection, simulation.py:255-260
 __global__ void __launch_bounds__(256) bl_apply_edits_kernel(const bl_system S, const double time,
                                                               const double *__restrict__ pos,
@@ -199,6 +213,13 @@ int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_
     bl_row_minima_kernel<<<(unsigned)((s->n + 7) / 8), 256, 0, st>>>(*s, d_toi, d_idx);
     h->launches++;
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_row_minima_kernel");
+}
+
+int bl_launch_snapshot(bl_handle *h, const bl_system *s, double time, double *d_out, cudaStream_t st) {
+    if (s->n <= 0) return BL_OK;
+    bl_snapshot_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(*s, time, d_out);
+    h->launches++;
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_snapshot_kernel");
 }
 
 int bl_launch_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, cudaStream_t st) {
