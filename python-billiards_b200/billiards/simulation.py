@@ -124,14 +124,20 @@ class Billiard:
             raw = np.frombuffer(bytes(recs), dtype=np.uint8).copy()
             new["obstacles"] = torch.from_numpy(raw).to(dev)
         self._dev, self._cap, self._pitch = new, cap, pitch
+        self._sys = None
 
     def _system(self):
+        """struct bl_system for the current buffers (cached: filling it costs 19 data_ptr() calls, ~15 us, which is a
+        good part of a short evolve call; dropped whenever a buffer or the ball count changes)"""
+        if getattr(self, "_sys", None) is not None:
+            return self._sys
         d = self._dev
         s = _lib.BlSystem()
         s.n, s.pitch, s.n_classes, s.n_obstacles = self._n, self._pitch, len(self._class_radii), len(self.obstacles)
         for name in ("p0x", "p0y", "vx", "vy", "t0", "radius", "mass", "rclass", "rsum2", "rsum2_obs", "obstacles",
                      "toi", "seq", "seq_counter", "cover_t", "cover_code", "obs_t", "obs_idx", "obs_arg"):
             setattr(s, name, d[name].data_ptr() if name in d else 0)
+        self._sys = s
         return s
 
     def _table_sync(self):
@@ -178,6 +184,7 @@ class Billiard:
             c = np.asarray([self._classes[x] for x in distinct], dtype=np.int32)[inv]
         else:
             c = np.asarray([self._classes[x] for x in radii], dtype=np.int32)
+        self._sys = None
         self._dev["radius"][first:last] = torch.from_numpy(r).to(dev)
         self._dev["rclass"][first:last] = torch.from_numpy(c).to(dev)
         self._radius_up[first:last] = self.balls_radius[first:last]
@@ -208,6 +215,7 @@ class Billiard:
         for q, name in enumerate(("p0x", "p0y", "vx", "vy", "t0")):
             d[name][first:last] = packed[q]
         self._n = last
+        self._sys = None
         self._radius_up.extend([None] * k)
         self._upload_radii(first, last)
         self._upload_masses()

@@ -33,6 +33,8 @@ __device__ __forceinline__ bool key_less(double ta, uint64_t ca, double tb, uint
     return ta < tb || (ta == tb && ca < cb);
 }
 
+// (measured: the same reduction as three REDUX.MIN over the order-preserving integer image of the time and a packed code
+// is slower -- pool shot 0.73 vs 0.71 ms, 2^18 pool tables 1.64 vs 1.83 G collisions/s)
 template <int W>
 __device__ __forceinline__ void group_min(unsigned gmask, double &t, uint64_t &c) {
 #pragma unroll
