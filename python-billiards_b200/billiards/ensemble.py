@@ -47,20 +47,24 @@ def _pinned(name, shape, dtype):
     return buf
 
 
-def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, device=None, dot_fma=None, chunks=4,
-                  count_hits=False):
-    """One-ball ensembles, host arrays in -> host arrays out, with the copies hidden behind the kernel.
+def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, mass=1.0, device=None, dot_fma=None,
+                  chunks=4, count_hits=False):
+    """Ensembles, host arrays in -> host arrays out, with the copies hidden behind the kernel.
 
     The systems are split into ``chunks`` contiguous blocks; block c goes host -> device, runs and comes back on its own
-    CUDA stream, so the copy engines work on one block while the SMs run the collision loop of another (the kernel is
-    bound by the FP64 pipe, the copies by PCIe).  Results are what ``BilliardEnsemble(...).run(n_collisions)`` gives
-    (systems are independent: the partition does not matter).  ``pos`` / ``vel`` should be pinned torch CPU tensors
-    (or numpy arrays: they are staged through a pinned buffer first).  Returns a dict of numpy arrays ``time`` (S,),
-    ``position`` (S, 2) (of the last collision), ``velocity`` (S, 2), ``counts`` (S,) and ``stats`` -- views of pinned
-    buffers that the next call overwrites.
+    CUDA stream, so the copy engines work on one block while the SMs run the collision loop of another (the kernels are
+    bound by instruction issue / the FP64 pipe, the copies by PCIe).  Results are what
+    ``BilliardEnsemble(...).run(n_collisions, end_time)`` gives (systems are independent: the partition does not matter).
+    ``pos`` / ``vel``: ``(S, 2)`` (one ball per system) or ``(S, n, 2)`` (n <= 32 balls per system; ``radius`` and ``mass``
+    per ball slot), ideally pinned torch CPU tensors (numpy arrays are staged through a pinned buffer first).  Returns a
+    dict of numpy arrays -- ``time`` (S,), ``position`` (of the last collision for one-ball systems, at each system's
+    clock otherwise), ``velocity``, ``counts`` (S,), ``stats`` -- views of pinned buffers that the next call overwrites.
     """
     import torch
-    pos_t, vel_t = _as_f64_tensor(pos).reshape(-1, 2), _as_f64_tensor(vel).reshape(-1, 2)
+    pos_t, vel_t = _as_f64_tensor(pos), _as_f64_tensor(vel)
+    multi = pos_t.dim() == 3
+    if not multi:
+        pos_t, vel_t = pos_t.reshape(-1, 2), vel_t.reshape(-1, 2)
     S = pos_t.shape[0]
     if not pos_t.is_pinned():
         pos_t = _pinned("in_pos", pos_t.shape, torch.float64).copy_(pos_t)
@@ -69,8 +73,8 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, d
     h = _lib.get_handle(device, dot_fma)
     dev = h.torch_device
     out_t = _pinned("out_t", (S,), torch.float64)
-    out_p = _pinned("out_p", (S, 2), torch.float64)
-    out_v = _pinned("out_v", (S, 2), torch.float64)
+    out_p = _pinned("out_p", tuple(pos_t.shape), torch.float64)
+    out_v = _pinned("out_v", tuple(pos_t.shape), torch.float64)
     out_c = _pinned("out_c", (S,), torch.int64)
     chunks = max(1, min(int(chunks), S))
     streams = _pinned_cache.setdefault(("streams", dev.index, chunks), [torch.cuda.Stream(dev) for _ in range(chunks)])
@@ -81,13 +85,20 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, d
         st = streams[c]
         st.wait_stream(start)
         with torch.cuda.stream(st):
-            ens = BilliardEnsemble(obstacles, pos_t[lo:hi], vel_t[lo:hi], radius=radius, device=dev.index,
+            ens = BilliardEnsemble(obstacles, pos_t[lo:hi], vel_t[lo:hi], radius=radius, mass=mass, device=dev.index,
                                    dot_fma=h.dot_fma, count_hits=count_hits)
             ens.run(n_collisions, end_time, sync=False)
-            out_t[lo:hi].copy_(ens._time, non_blocking=True)
-            out_p[lo:hi].copy_(ens._state[0:2].T, non_blocking=True)
-            out_v[lo:hi].copy_(ens._state[2:4].T, non_blocking=True)
-            out_c[lo:hi].copy_(ens._counts, non_blocking=True)
+            if multi:
+                d = ens._dev
+                out_t[lo:hi].copy_(d["time"], non_blocking=True)
+                out_p[lo:hi].copy_(ens._positions_device(0.0, 1), non_blocking=True)
+                out_v[lo:hi].copy_(torch.stack([d["vx"], d["vy"]], dim=-1), non_blocking=True)
+                out_c[lo:hi].copy_(d["n_ball_ball"] + d["n_ball_obstacle"], non_blocking=True)
+            else:
+                out_t[lo:hi].copy_(ens._time, non_blocking=True)
+                out_p[lo:hi].copy_(ens._state[0:2].T, non_blocking=True)
+                out_v[lo:hi].copy_(ens._state[2:4].T, non_blocking=True)
+                out_c[lo:hi].copy_(ens._counts, non_blocking=True)
             parts.append(ens)
     for st in streams:
         start.wait_stream(st)  # the caller's stream continues after every block is back
@@ -96,7 +107,7 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, d
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
     total = total.cpu()  # synchronises the current stream, which waited for every chunk
-    bad = sum(int((p._status != 0).sum().item()) for p in parts)
+    bad = sum(int(((p._dev["status"] if multi else p._status) != 0).sum().item()) for p in parts)
     if bad:
         raise ValueError(f"{bad} systems hit a separating/degenerate collision (status != 0)")
     return {"time": out_t.numpy(), "position": out_p.numpy(), "velocity": out_v.numpy(), "counts": out_c.numpy(),
@@ -319,14 +330,17 @@ class BilliardEnsemble:
             return np.stack([s[0] + s[2] * dt, s[1] + s[3] * dt], axis=1)
         return self._positions(0.0, 1)
 
-    def _positions(self, time, at_system_time):
+    def _positions_device(self, time, at_system_time):
         import torch
         h = self._handle
         out = torch.empty((self.n, self.balls_per_system, 2), dtype=torch.float64, device=h.torch_device)
         m = self._multi_struct()
         h.check(h.lib.bl_multi_positions(h.h, ctypes.byref(m), float(time), int(at_system_time), _lib.ptr(out),
                                          h.stream()))
-        return _lib.to_host(out)
+        return out
+
+    def _positions(self, time, at_system_time):
+        return _lib.to_host(self._positions_device(time, at_system_time))
 
     @property
     def toi_tables(self):

@@ -312,6 +312,40 @@ def test_full_size_pool_ensemble(billiards, golden):
     assert ens.gather_stats().tolist() == [S * 415, S * 167, S * 248]
 
 
+def test_run_from_host_matches_the_resident_path(billiards):
+    """ensemble.run_from_host (blocks of systems pipelined over streams, pinned buffers) == BilliardEnsemble.run on the
+    whole set, for one-ball and multi-ball systems: the partition into blocks must not change a bit."""
+    from billiards import _lib
+    from billiards.ensemble import run_from_host
+    fma = _lib.probe_dot_fma()
+    obstacles, pos, vel = workloads.sinai(5001, seed=9)
+    obs = workloads.make_obstacles(billiards, obstacles)
+    ens = billiards.BilliardEnsemble(obs, pos, vel, dot_fma=fma)
+    ens.run(300)
+    for chunks in (1, 3, 4):
+        out = run_from_host(obs, pos, vel, 300, dot_fma=fma, chunks=chunks)
+        assert_bits_equal(out["time"], ens.time, f"{chunks} chunks")
+        assert_bits_equal(out["velocity"], ens.balls_velocity, f"{chunks} chunks")
+        assert_bits_equal(out["position"], ens.balls_initial_position, f"{chunks} chunks")
+        assert out["counts"].tolist() == ens.counts.tolist() and int(out["stats"][0]) == 5001 * 300
+    cfg = workloads.pool()
+    S = 37
+    rng = np.random.default_rng(12)
+    mpos = np.repeat(cfg.pos[None], S, axis=0)
+    mvel = np.repeat(cfg.vel[None], S, axis=0)
+    mvel[:, 15, 0] *= rng.uniform(0.7, 1.3, S)
+    mvel[:, 15, 1] = mvel[:, 15, 0] * rng.uniform(-0.03, 0.03, S)
+    pobs = workloads.make_obstacles(billiards, cfg.obstacles)
+    whole = billiards.BilliardEnsemble(pobs, mpos, mvel, radius=cfg.radius, mass=cfg.mass, dot_fma=fma)
+    whole.run(-1, end_time=100.0)
+    out = run_from_host(pobs, mpos, mvel, -1, end_time=100.0, radius=cfg.radius, mass=cfg.mass, dot_fma=fma, chunks=4)
+    assert_bits_equal(out["time"], whole.time)
+    assert_bits_equal(out["velocity"], whole.balls_velocity)
+    assert_bits_equal(out["position"], whole.balls_position)
+    assert out["counts"].tolist() == whole.counts.tolist()
+    assert out["stats"].tolist() == whole.gather_stats().tolist()
+
+
 def test_library_calls_on_a_non_current_device(billiards, oracle):
     """A Billiard and both ensemble kinds on cuda:1 while cuda:0 is torch's current device (every C entry makes the
     handle's device current for the call)."""
