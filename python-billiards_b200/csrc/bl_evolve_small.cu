@@ -73,8 +73,11 @@ __device__ __forceinline__ void row_min(const double *Trow, double &best, int &b
     }
 }
 
+// Ensemble launches: six CTAs of four warps per SM (80 registers, a few spilled words outside the hot path) -- the loop
+// is a chain of long-latency steps, and 24 resident warps hide it better than the 16 that the compiler's own 127
+// registers allow: 1.79 -> 1.99 G collisions/s on 2^16 pool tables (seven and eight CTAs per SM measure the same).
 template <bool FMA, int W, bool SINGLE>
-__global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, 1)
+__global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 : 6)
     bl_evolve_small_kernel(const __grid_constant__ SmallParams P) {
     // one table row per lane: row (warp, lane) = T[ball li of that lane's system][0..W), padded to W + 1 (odd pitch:
     // the 32 lanes of a warp hit distinct banks whatever W is)
