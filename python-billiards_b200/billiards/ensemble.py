@@ -244,13 +244,15 @@ class BilliardEnsemble:
                         _lib.BL_ENAN: "a NaN impact time"}.get(code, f"status {code}")
                 raise ValueError(f"{bad} systems stopped early, first: system {first}: {what}")
 
-    def evolve(self, end_time):
+    def evolve(self, end_time, max_collisions=None):
         """Every system runs ``Billiard.evolve(end_time)``; returns the (ball-ball, ball-obstacle) collision counts of
-        this call per system as two int64 arrays."""
+        this call per system as two int64 arrays.  ``max_collisions`` bounds the collisions of each system in this call
+        (a safety valve: some set-ups collide infinitely often in finite time, and a kernel cannot be interrupted);
+        a system that reaches it stops at its last collision, ``time`` tells which."""
         if not self._multi:
             raise TypeError("evolve(end_time) is for multi-ball ensembles; one-ball ensembles use run()")
         before_bb, before_bo = self._dev["n_ball_ball"].clone(), self._dev["n_ball_obstacle"].clone()
-        self._run_multi(-1, end_time, True)
+        self._run_multi(-1 if max_collisions is None else int(max_collisions), end_time, True)
         return (_lib.to_host(self._dev["n_ball_ball"] - before_bb), _lib.to_host(self._dev["n_ball_obstacle"] - before_bo))
 
     # ================================================================================================

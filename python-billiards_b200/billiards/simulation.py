@@ -494,6 +494,12 @@ class Billiard:
     callback_mode = "replay"
     #: collisions logged per launch in replay mode (the launch stops when the log is full and is continued)
     callback_log_capacity = 1 << 16
+    #: safety valve for ``evolve``: None = no limit, like the reference.  Some set-ups collide infinitely often in finite
+    #: time (a zero-mass ball squeezed between two heavy ones, a moving infinite mass pressing a ball against a wall, a
+    #: radius-0 ball on a LineSegment); ``evolve(end_time)`` then never returns -- in the reference a Ctrl-C away, here
+    #: inside a kernel that cannot be interrupted.  With a limit, ``evolve`` raises RuntimeError after that many
+    #: collisions in one call (the state is left at the last handled collision, bit-exact and resumable).
+    evolve_event_limit = None
 
     def _log_buffers(self, cap):
         """Device event log (t, i, j, payload[12]) as ONE allocation plus a pinned host mirror, cached per Billiard."""
@@ -562,10 +568,14 @@ class Billiard:
             if any(not isinstance(key, Obstacle) for key in obstacle_callbacks):
                 raise ValueError("Keys of 'obstacle_callbacks' must be instances of Obstacle")
 
+        limit = -1 if self.evolve_event_limit is None else int(self.evolve_event_limit)
         if time_callback is None and not ball_callbacks and not obstacle_callbacks:
-            res = self._run(end_time)
+            res = self._run(end_time, max_events=limit)
             if res.stop == _lib.BL_STOP_TIME:
                 self._time = end_time  # keep the caller's number (the reference stores end_time itself)
+            elif res.stop == _lib.BL_STOP_EVENTS:
+                raise RuntimeError(f"evolve_event_limit: {limit} collisions handled and t = {self._time} < end_time = "
+                                   f"{end_time}; collisions accumulating in finite time?")
             return (int(res.n_ball_ball), int(res.n_ball_obstacle))
 
         n_bb = n_bo = 0
