@@ -396,3 +396,26 @@ def test_mass_edit_is_seen_without_recompute(bl):
     b.balls_mass[1] = INF
     b.evolve(4.0)
     assert tuple(b.balls_velocity[0]) == (-1, 0) and tuple(b.balls_velocity[1]) == (0, 0)
+
+
+def test_evolve_event_limit_stops_an_accumulation_of_collisions(bl):
+    """A zero-mass ball between two approaching heavy balls collides infinitely often in finite time: evolve(end_time)
+    never returns in the reference (nor would the kernel).  With Billiard.evolve_event_limit the call raises after that
+    many collisions and leaves a resumable state; BilliardEnsemble.evolve(max_collisions=) bounds each system."""
+    bld = bl.Billiard()
+    bld.add_ball((0.0, 0.0), (1.0, 0.0), radius=1.0, mass=10.0)
+    bld.add_ball((5.0, 0.0), (0.0, 0.0), radius=0.1, mass=0.0)
+    bld.add_ball((10.0, 0.0), (-1.0, 0.0), radius=1.0, mass=10.0)
+    bld.evolve_event_limit = 3000
+    with pytest.raises(RuntimeError):
+        bld.evolve(100.0)
+    assert bld.time < 100.0 and np.isfinite(bld.balls_position).all()
+    t = bld.time
+    with pytest.raises(RuntimeError):
+        bld.evolve(100.0)            # resumable: the next 3000 collisions
+    assert bld.time >= t
+    pos = np.repeat(np.asarray([[(0.0, 0.0), (5.0, 0.0), (10.0, 0.0)]]), 4, axis=0)
+    vel = np.repeat(np.asarray([[(1.0, 0.0), (0.0, 0.0), (-1.0, 0.0)]]), 4, axis=0)
+    ens = bl.BilliardEnsemble([], pos, vel, radius=[1.0, 0.1, 1.0], mass=[10.0, 0.0, 10.0])
+    bb, bo = ens.evolve(100.0, max_collisions=2500)
+    assert (bb == 2500).all() and (bo == 0).all() and (ens.time < 100.0).all()
