@@ -4,10 +4,11 @@
 // consecutive collisions share balls, a batch would hold one collision -- so the grid-wide round machinery of
 // bl_evolve.cu buys nothing there.  Here a system of n balls is served by W = 2, 4, 8, 16 or 32 lanes of one warp
 // (the smallest power of two >= n): lane i owns ball i (state of record in registers), the system's whole
-// time-of-impact table sits in shared memory (both triangles current), and one collision is: row minima -> group
-// argmin (xor butterfly over the W lanes) -> every lane resolves the collision redundantly from shuffled states ->
-// every other lane re-solves its pair(s) with the colliding ball(s) -> the colliding lanes refresh their obstacle
-// entry.  No barrier but __syncwarp on the group's lanes.
+// time-of-impact table sits in shared memory (both triangles current), and one collision is: row minima (compare
+// tree) -> group argmin (xor butterfly over the W lanes) -> every lane resolves the collision redundantly from
+// shuffled states -> every other lane re-solves its pair(s) with the colliding ball(s) -> the (ball, obstacle) solves
+// of the colliding balls are spread over the lanes and combined by a second butterfly.  No barrier but __syncwarp on
+// the group's lanes.
 //
 // The same kernel serves
 //   * a single Billiard (bl_evolve / bl_next on a bl_system with n <= 32): SINGLE = true, one group, with the
