@@ -94,6 +94,10 @@ class ClockSampler:
         if self.proc is None:
             return None
         time.sleep(0.15)
+        for _ in range(8):  # a timed region shorter than the sampling period: wait for the first sample
+            if self.rows:
+                break
+            time.sleep(0.1)
         self.proc.terminate()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         if not sm:
