@@ -89,7 +89,13 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int li = lane & (W - 1);                      // my ball
     const int gbase = lane & ~(W - 1);                  // first lane of my group
-    const unsigned gmask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << gbase);
+    // Every shuffle, vote and __syncwarp names the whole warp: the groups of a warp run the collision loop in lockstep
+    // (a group that is done idles until the last one is), so the warp is converged wherever they are issued.  With a
+    // per-group mask -- a run-time value that differs between the lanes of a warp -- the compiler wraps every one of
+    // them in MATCH.ANY + REDUX.OR + VOTEU sequences (7 of each per iteration in the first version of this kernel, 6 %
+    // of its stall samples on the MATCH alone).  Threads that have exited do not count as participants.
+    constexpr unsigned gmask = 0xffffffffu;
+    (void)gbase;
     double *const Tw = smem + (size_t)warp * 32 * RP;   // this warp's rows
     double *const Trow = Tw + (size_t)lane * RP;        // my row
     double *const Tg = Tw + (size_t)gbase * RP;         // row 0 of my group: row of ball a = Tg + a * RP
@@ -153,12 +159,13 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
         if (P.query_only) { final_stage = 1; kindmask = KIND_BB; }
     }
     int end_stop = BL_STOP_TIME, end_status = BL_OK;
+    bool fin = false;  // ensembles: my system has stopped (its group keeps pace with the others of the warp)
 
     for (;;) {
         // ---- my key: minimum of my table row (first index on ties), or my next obstacle ----
         double kt = BL_INF;
         uint64_t kc = BL_CODE_END;
-        if (own) {
+        if (own && !fin) {
             if (kindmask != KIND_BO) {
                 int bj;
                 row_min<W>(Trow, kt, bj);
@@ -189,18 +196,19 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
         double ax = 0, ay = 0, avx = 0, avy = 0, bx = 0, by = 0, bvx = 0, bvy = 0;
         double a_vx = 0, a_vy = 0, b_vx = 0, b_vy = 0, qarg = 0;
         int oi = -1, rca = 0, rcb = 0;
+        // the states of the two balls come by shuffle (issued by every lane of the warp, whatever its group decides)
+        const int sa = a >= 0 ? a : 0, sb2 = b >= 0 ? b : sa;
+        const double a0x = __shfl_sync(gmask, p0x, sa, W), a0y = __shfl_sync(gmask, p0y, sa, W);
+        const double a_t0 = __shfl_sync(gmask, t0, sa, W), am = __shfl_sync(gmask, mass, sa, W);
+        a_vx = __shfl_sync(gmask, vx, sa, W); a_vy = __shfl_sync(gmask, vy, sa, W);
+        const double b0x = __shfl_sync(gmask, p0x, sb2, W), b0y = __shfl_sync(gmask, p0y, sb2, W);
+        const double b_t0 = __shfl_sync(gmask, t0, sb2, W), bm = __shfl_sync(gmask, mass, sb2, W);
+        b_vx = __shfl_sync(gmask, vx, sb2, W); b_vy = __shfl_sync(gmask, vy, sb2, W);
+        qarg = __shfl_sync(gmask, oarg, sa, W);
+        oi = __shfl_sync(gmask, oidx, sa, W);
+        rca = __shfl_sync(gmask, rc, sa, W); rcb = __shfl_sync(gmask, rc, sb2, W);
         if (stop_kind < 0) {
-            // ---- resolve, redundantly in every lane of the group (states come by shuffle) ----
-            const int sa = a, sb2 = b >= 0 ? b : a;
-            const double a0x = __shfl_sync(gmask, p0x, sa, W), a0y = __shfl_sync(gmask, p0y, sa, W);
-            const double a_t0 = __shfl_sync(gmask, t0, sa, W), am = __shfl_sync(gmask, mass, sa, W);
-            a_vx = __shfl_sync(gmask, vx, sa, W); a_vy = __shfl_sync(gmask, vy, sa, W);
-            const double b0x = __shfl_sync(gmask, p0x, sb2, W), b0y = __shfl_sync(gmask, p0y, sb2, W);
-            const double b_t0 = __shfl_sync(gmask, t0, sb2, W), bm = __shfl_sync(gmask, mass, sb2, W);
-            b_vx = __shfl_sync(gmask, vx, sb2, W); b_vy = __shfl_sync(gmask, vy, sb2, W);
-            qarg = __shfl_sync(gmask, oarg, sa, W);
-            oi = __shfl_sync(gmask, oidx, sa, W);
-            rca = __shfl_sync(gmask, rc, sa, W); rcb = __shfl_sync(gmask, rc, sb2, W);
+            // ---- resolve, redundantly in every lane of the group ----
             ax = bl_advance(a0x, a_vx, t, a_t0); ay = bl_advance(a0y, a_vy, t, a_t0);
             int st;
             if (b < 0) {
@@ -219,8 +227,12 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
                 now = t;
             }
         }
-        if (stop_kind >= 0) {
-            if (!SINGLE) { end_stop = stop_kind; end_status = st_status; break; }
+        if (!SINGLE) {
+            if (stop_kind >= 0 && !fin) { end_stop = stop_kind; end_status = st_status; fin = true; }
+            if (__all_sync(gmask, fin)) break;
+        }
+        const bool act = stop_kind < 0;  // my group handles a collision in this iteration
+        if (SINGLE && stop_kind >= 0) {
             if (final_stage == 0) {
                 if (li == 0) {
                     double tnow = now;
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
                 else { o[6] = qarg; o[7] = 0; o[8] = 0; o[9] = 0; o[10] = 0; o[11] = 0; }
             }
         }
-        if (own && li != a && li != b) {
+        if (act && own && li != a && li != b) {
             // ---- every other ball re-solves its pair with the colliding ball(s); simulation.py:461-471, :522-526 ----
             const double px = bl_advance(p0x, vx, t, t0), py = bl_advance(p0y, vy, t, t0);
             // both quadratics of physics.py:33-54 side by side (two independent chains), then the square root and the
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
                 vb = bl_add(t, vb);
                 Trow[b] = vb; Tg[b * RP + li] = vb;
             }
-        } else if (own) {
+        } else if (act && own) {
             // ---- the colliding balls: new state of record, pair entry = inf (:458) ----
             if (li == a) { p0x = ax; p0y = ay; vx = avx; vy = avy; }
             else { p0x = bx; p0y = by; vx = bvx; vy = bvy; }
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
         // the reference's strict < in list order ----
         {
             const int which = li & 1;
-            const int tball = which ? b : a;
+            const int tball = act ? (which ? b : a) : -1;
             const double tx = which ? bx : ax, ty = which ? by : ay, tvx = which ? bvx : avx, tvy = which ? bvy : avy;
             const int src = tball >= 0 ? tball : 0;
             const double tradius = __shfl_sync(gmask, radius, src, W);
@@ -338,13 +350,15 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             const int q_a = __shfl_sync(gmask, oq, 0, W);
             const double t_b = __shfl_sync(gmask, omin, 1, W), g_b = __shfl_sync(gmask, oam, 1, W);
             const int q_b = __shfl_sync(gmask, oq, 1, W);
-            if (li == a) { ot = bl_add(t, t_a); oidx = q_a; oarg = g_a; }
-            if (li == b) { ot = bl_add(t, t_b); oidx = q_b; oarg = g_b; }
+            if (act && li == a) { ot = bl_add(t, t_a); oidx = q_a; oarg = g_a; }
+            if (act && li == b) { ot = bl_add(t, t_b); oidx = q_b; oarg = g_b; }
         }
         __syncwarp(gmask);
-        done++;
-        n_bb += b >= 0 ? 1 : 0;
-        now = t;
+        if (act) {
+            done++;
+            n_bb += b >= 0 ? 1 : 0;
+            now = t;
+        }
         kindmask = KIND_BOTH;  // only the first event's kind was forced
     }
 
