@@ -144,7 +144,15 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
     }
     __syncwarp(gmask);
 
-    const bool want_log = SINGLE && P.log.cap > 0;
+    bool want_log = SINGLE && P.log.cap > 0;
+    bool k_one = K == 1;  // one radius class: (r_a + r_b)**2 is one number
+    int n_obs_r = n_obs;
+    {
+        // loop invariants as opaque register values, not constant-bank reloads + compares inside the loop
+        int wl = want_log ? 1 : 0, ko = k_one ? 1 : 0;
+        asm volatile("" : "+r"(wl), "+r"(ko), "+r"(n_obs_r));
+        want_log = wl != 0; k_one = ko != 0;
+    }
     // the limits as opaque register values (re-reading kernel parameters from the constant bank inside the loop costs a
     // load, a compare and a branch each time): collisions this launch may handle, room in the log, last admissible time
     long long max_ev = P.max_events >= 0 ? P.max_events : 0x7fffffffffffffffLL;
@@ -283,7 +291,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             const double px = bl_advance(p0x, vx, t, t0), py = bl_advance(p0y, vy, t, t0);
             // both quadratics of physics.py:33-54 side by side (two independent chains), then the square root and the
             // division only for a pair that gets past the two early exits
-            const double rsa = K == 1 ? rs_one : rs_row[rca];
+            const double rsa = k_one ? rs_one : rs_row[rca];
             const double dax = bl_sub(px, ax), day = bl_sub(py, ay), dvax = bl_sub(vx, avx), dvay = bl_sub(vy, avy);
             const double qb_a = bl_dot2<FMA>(dax, day, dvax, dvay);
             const double qc_a = bl_sub(bl_dot2<FMA>(dax, day, dax, day), rsa);
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             double va = BL_INF, vb = BL_INF;
             double qb_b = 0.0, qc_b = 0.0, qd_b = 0.0;
             if (b >= 0) {
-                const double rsb = K == 1 ? rs_one : rs_row[rcb];
+                const double rsb = k_one ? rs_one : rs_row[rcb];
                 const double dbx = bl_sub(px, bx), dby = bl_sub(py, by), dvbx = bl_sub(vx, bvx), dvby = bl_sub(vy, bvy);
                 qb_b = bl_dot2<FMA>(dbx, dby, dvbx, dvby);
                 qc_b = bl_sub(bl_dot2<FMA>(dbx, dby, dbx, dby), rsb);
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             double omin = BL_INF, oam = 0.0;
             int oq = -1;
             if (tball >= 0) {
-                for (int q = li >> 1; q < n_obs; q += (W > 2 ? W / 2 : 1)) {
+                for (int q = li >> 1; q < n_obs_r; q += (W > 2 ? W / 2 : 1)) {
                     double arg;
                     const double rs = s_obs[q].kind != BL_OBS_WALL ? P.rsum2_obs[(size_t)q * K + trc] : 0.0;
                     const double tq = bl_obstacle_toi<FMA>(s_obs[q], tx, ty, tvx, tvy, tradius, rs, arg);
