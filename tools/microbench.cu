@@ -29,6 +29,32 @@ __global__ void barrier_kernel(unsigned *bar, unsigned *flags, int iters, long l
                 atomicAdd(bar, 1u);
                 while ((int)(ld_acquire_u32(bar) - epoch) < 0) { if (MODE == 1) __nanosleep(40); }
             }
+        } else if (MODE == 3) {
+            // release folded into the arrival (no separate fence, no returned value), relaxed polling, one acquire fence
+            if (threadIdx.x == 0) {
+                epoch += ncta;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+                unsigned v;
+                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - epoch) < 0);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
+        } else if (MODE == 4) {
+            // release arrival, acquire polling (no fences)
+            if (threadIdx.x == 0) {
+                epoch += ncta;
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+                while ((int)(ld_acquire_u32(bar) - epoch) < 0) {}
+            }
+        } else if (MODE == 5) {
+            // fence + relaxed atomic arrival (as mode 0), relaxed polling, acquire fence at the end
+            if (threadIdx.x == 0) {
+                epoch += ncta;
+                __threadfence();
+                atomicAdd(bar, 1u);
+                unsigned v;
+                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - epoch) < 0);
+                __threadfence();
+            }
         } else {
             __shared__ int last;
             if (threadIdx.x == 0) {
@@ -106,11 +132,13 @@ int main() {
     cudaMalloc(&sink, 148 * 1024 * 8);
     const int iters = 2000;
     for (int ncta : {16, 64, 128, 148}) {
-        for (int mode = 0; mode < 3; mode++) {
+        for (int mode = 0; mode < 6; mode++) {
             cudaMemset(bar, 0, 64);
             cudaMemset(flags, 0, 256 * 128);
             void *args[] = {&bar, &flags, (void *)&iters, &out};
-            const void *fn = mode == 0 ? (const void *)barrier_kernel<0> : mode == 1 ? (const void *)barrier_kernel<1> : (const void *)barrier_kernel<2>;
+            const void *fn = mode == 0 ? (const void *)barrier_kernel<0> : mode == 1 ? (const void *)barrier_kernel<1>
+                           : mode == 2 ? (const void *)barrier_kernel<2> : mode == 3 ? (const void *)barrier_kernel<3>
+                           : mode == 4 ? (const void *)barrier_kernel<4> : (const void *)barrier_kernel<5>;
             cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(ncta), dim3(128), args, 0, 0);
             cudaDeviceSynchronize();
             cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost);
