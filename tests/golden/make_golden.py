@@ -209,6 +209,10 @@ def main():
     if args.big and want("dense16384"):
         logged_case(ref, dot_fma, workloads.dense_gas(128), "dense_gas_16384", n_events=100)
 
+    # ---- X: the collapsing cloud (examples/collapse.py): 200 balls, no obstacles --------------------------
+    if want("collapse"):
+        logged_case(ref, dot_fma, workloads.collapse(), "collapse", end_time=15.0)
+
     # ---- C: Newton's cradle (docs/usage.rst:80-158) --------------------------------------------------
     if want("cradle"):
         cfg = workloads.newtons_cradle(5, True)

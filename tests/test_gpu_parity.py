@@ -36,6 +36,7 @@ LOGGED = [
     ("dense_gas_16384", lambda: workloads.dense_gas(128), dict(n_events=100)),
     ("maze", workloads.maze, dict(n_events=3000)),            # LineSegment obstacles (examples/maze.py)
     ("maze_wide", workloads.maze_wide, dict(n_events=4000)),  # all four segments, both faces, end points
+    ("collapse", workloads.collapse, dict(end_time=15.0)),    # no obstacles at all (examples/collapse.py)
 ]
 
 

@@ -28,6 +28,7 @@ LOGGED = [
     ("ideal_gas_1024", lambda: workloads.ideal_gas(32), dict(n_events=1000)),
     ("maze", workloads.maze, dict(n_events=3000)),            # LineSegment obstacles, examples/maze.py
     ("maze_wide", workloads.maze_wide, dict(n_events=4000)),  # all four segments, both faces, end points
+    ("collapse", workloads.collapse, dict(end_time=15.0)),    # no obstacles at all (examples/collapse.py)
 ]
 
 

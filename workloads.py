@@ -248,6 +248,20 @@ def maze_wide(num_balls=150, radius=0.02, seed=7):
     return Config("maze_wide", MAZE_OBSTACLES, pos, vel, radius, 1.0)
 
 
+def collapse(num_balls=200):
+    """Config X: examples/collapse.py:11-26 -- a cloud of unit balls falling towards the origin in free space (no
+    obstacle at all); the example calls np.random.seed(0) and draws position then velocity per ball."""
+    rs = np.random.RandomState(0)
+    pos, vel = [], []
+    for _ in range(num_balls):
+        p = rs.normal(0, scale=1, size=2)
+        v = rs.normal(0, scale=5, size=2)
+        p -= v * 10
+        pos.append(p)
+        vel.append(v)
+    return Config("collapse", [], pos, vel, 1.0, 1.0, end_time=15.0)
+
+
 def newtons_cradle(num_balls=5, with_walls=True):
     """Config C: the fixture of the reference's tests (tests/conftest.py:7-28)."""
     obstacles = []
