@@ -419,3 +419,33 @@ def test_evolve_event_limit_stops_an_accumulation_of_collisions(bl):
     ens = bl.BilliardEnsemble([], pos, vel, radius=[1.0, 0.1, 1.0], mass=[10.0, 0.0, 10.0])
     bb, bo = ens.evolve(100.0, max_collisions=2500)
     assert (bb == 2500).all() and (bo == 0).all() and (ens.time < 100.0).all()
+
+
+# ---- the reference's example scripts, headless ------------------------------------------------------------
+EXAMPLE_COUNTS = {
+    # collisions the live reference counts for the same set-up (tests/golden: collapse 2403 events to t = 15, Galperin's
+    # 314159); the others are pinned by the frames-equal-one-call property below
+    "collapse": 2403, "pi_with_pool": 314159,
+}
+
+
+@pytest.mark.parametrize("name", ["collapse", "ideal_gas", "maze", "newtons_cradle", "pi_with_pool", "pool_first_shot",
+                                  "sinai_billiard"])
+def test_reference_examples_run_headless(bl, name):
+    """examples/*.py of the reference through examples/headless.py: advanced frame by frame the way visualize.animate
+    does (evolve(t + dt), read positions and velocities) and in one evolve(end_time) call -- same counts, same bits."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "headless.py")
+    spec = importlib.util.spec_from_file_location("examples_headless", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    frames = mod.run(name)
+    once = mod.run(name, 0.0)
+    assert frames["frames"] > 100 and once["frames"] == 1
+    for key in ("balls", "end_time", "ball_ball", "ball_obstacle", "mean_speed", "kinetic_energy", "position_checksum"):
+        assert frames[key] == once[key], key
+    if name in EXAMPLE_COUNTS:
+        assert frames["ball_ball"] + frames["ball_obstacle"] == EXAMPLE_COUNTS[name]
+    if name == "pool_first_shot":
+        assert frames["ball_ball"] + frames["ball_obstacle"] > 100
