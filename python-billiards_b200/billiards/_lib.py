@@ -79,6 +79,8 @@ SIGNATURES = {
     "bl_row_minima": (ctypes.c_int, [_H, _SYS, c_void, c_void, c_void]),
     "bl_evolve": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int,
                                  ctypes.POINTER(BlLog), ctypes.POINTER(BlResult), c_void]),
+    "bl_evolve_snapshot": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int,
+                                          ctypes.POINTER(BlLog), ctypes.POINTER(BlResult), c_void, c_void, c_void]),
     "bl_next": (ctypes.c_int, [_H, _SYS, ctypes.c_double, ctypes.POINTER(BlResult), c_void]),
     "bl_snapshot": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void, c_void]),
     "bl_positions": (ctypes.c_int, [_H, _SYS, ctypes.c_double, c_void, c_void]),

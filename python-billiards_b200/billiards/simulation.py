@@ -216,6 +216,7 @@ class Billiard:
             d[name][first:last] = packed[q]
         self._n = last
         self._sys = None
+        self._snap_fresh = False
         self._radius_up.extend([None] * k)
         self._upload_radii(first, last)
         self._upload_masses()
@@ -241,18 +242,31 @@ class Billiard:
         if n:
             # one launch + one device -> pinned-host copy (bl_snapshot); the mirrors are fresh arrays, like the
             # reference's, so that references a caller kept to earlier arrays stay what they were
-            snap = getattr(self, "_snap", None)
-            if snap is None or snap[0] < n:
-                cap = max(n, 2 * (snap[0] if snap else 0))
-                snap = (cap, torch.empty(8 * cap, dtype=torch.float64, device=h.torch_device),
-                        torch.empty(8 * cap, dtype=torch.float64, pin_memory=True))
-                self._snap = snap
-            s = self._system()
-            h.check(h.lib.bl_snapshot(h.h, ctypes.byref(s), float(self._time), _lib.ptr(snap[1]),
-                                      ctypes.c_void_p(snap[2].data_ptr()), h.stream()))
+            snap = self._snap_buffers(n)
+            if not self._snap_fresh:  # (an evolve call leaves the snapshot behind: nothing to launch then)
+                s = self._system()
+                h.check(h.lib.bl_snapshot(h.h, ctypes.byref(s), float(self._time), _lib.ptr(snap[1]),
+                                          ctypes.c_void_p(snap[2].data_ptr()), h.stream()))
             block = snap[2].numpy()[:8 * n].reshape(4, n, 2).copy()
             self._pos, self._vel, self._p0, self._t0 = block[0], block[1], block[2], block[3]
+        self._snap_fresh = False
         self._host_valid = True
+
+    #: set by an evolve launch that left the host mirrors' snapshot in the pinned buffer (same stream, same wait)
+    _snap_fresh = False
+    _snap = None
+
+    def _snap_buffers(self, n):
+        """[4][n][2] doubles on the device and page-locked on the host, grown geometrically, cached per Billiard."""
+        import torch
+        snap = self._snap
+        if snap is None or snap[0] < n:
+            cap = max(n, 2 * (snap[0] if snap else 0))
+            snap = (cap, torch.empty(8 * cap, dtype=torch.float64, device=self._h().torch_device),
+                    torch.empty(8 * cap, dtype=torch.float64, pin_memory=True))
+            self._snap = snap
+            self._snap_fresh = False
+        return snap
 
     # ------------------------------------------------------------------------------------------------
     # attributes of the reference class
@@ -443,6 +457,7 @@ class Billiard:
         h.check(h.lib.bl_rebuild_cover(h.h, ctypes.byref(s), h.stream()))
         self._next = None
         self._host_valid = False
+        self._snap_fresh = False
 
     def _detect_ball_collision(self, idx1, idx2):
         """Absolute time of impact of two balls of the simulation (simulation.py:311-330)."""
@@ -467,8 +482,20 @@ class Billiard:
         h = self._h()
         res = _lib.BlResult()
         s = self._system()
-        rc = h.lib.bl_evolve(h.h, ctypes.byref(s), float(self._time), float(end_time), int(max_events), int(first_kind),
-                             ctypes.byref(log) if log is not None else None, ctypes.byref(res), h.stream())
+        self._snap_fresh = False
+        if self._n:
+            # evolve + the snapshot of the host mirrors at the clock it stops at, one wait for both: the frame loop of
+            # visualize_*.animate reads balls_position / balls_velocity after every evolve call
+            snap = self._snap_buffers(self._n)
+            rc = h.lib.bl_evolve_snapshot(h.h, ctypes.byref(s), float(self._time), float(end_time), int(max_events),
+                                          int(first_kind), ctypes.byref(log) if log is not None else None,
+                                          ctypes.byref(res), _lib.ptr(snap[1]), ctypes.c_void_p(snap[2].data_ptr()),
+                                          h.stream())
+            self._snap_fresh = rc == _lib.BL_OK
+        else:
+            rc = h.lib.bl_evolve(h.h, ctypes.byref(s), float(self._time), float(end_time), int(max_events),
+                                 int(first_kind), ctypes.byref(log) if log is not None else None, ctypes.byref(res),
+                                 h.stream())
         self.last_result = res
         if res.n_ball_ball + res.n_ball_obstacle:
             self._table_dirty = True

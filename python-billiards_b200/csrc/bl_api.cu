@@ -178,7 +178,8 @@ int bl_row_minima(bl_handle *h, const bl_system *s, double *d_balls_toi, int64_t
 }
 
 static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
-                      int first_kind, const bl_log *log, int query_only, bl_result *out, void *stream) {
+                      int first_kind, const bl_log *log, int query_only, bl_result *out, void *stream,
+                      double *d_snap = nullptr, double *host_snap = nullptr) {
     bl_entry_guard g(h);
     int rc = check_system(h, s);
     if (rc) return rc;
@@ -198,8 +199,33 @@ static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_
     rc = bl_launch_evolve(h, s, time, end_time, max_events, first_kind, log, query_only, st);
     if (rc) return rc;
     cudaEventRecord(h->ev1, st);
-    cudaError_t e = cudaMemcpyAsync(h->h_result, h->d_result, sizeof(bl_result), cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return bl_check_cuda(h, e, "copy result");
+    cudaError_t e;
+    bool direct = false;
+    if (d_snap) {
+        // the host mirrors at the clock the kernel stopped at, behind the kernel on the same stream: one wait for both.
+        // Page-locked host memory is written by the snapshot kernel itself, the result block with it: no copy
+        // operation (each one a few microseconds of latency) between the kernels and the wait.
+        double *snap_dev = nullptr;
+        bl_result *res_dev = nullptr;
+        if (host_snap) {
+            if (cudaHostGetDevicePointer((void **)&snap_dev, host_snap, 0) == cudaSuccess &&
+                cudaHostGetDevicePointer((void **)&res_dev, h->h_result, 0) == cudaSuccess)
+                direct = true;
+            else
+                (void)cudaGetLastError();  // pageable host memory: staged copies below
+        }
+        rc = bl_launch_snapshot(h, s, 0.0, &h->d_result->time, d_snap, st, direct ? snap_dev : nullptr,
+                                direct ? h->d_result : nullptr, direct ? res_dev : nullptr);
+        if (rc) return rc;
+        if (host_snap && !direct) {
+            e = cudaMemcpyAsync(host_snap, d_snap, sizeof(double) * 8 * (size_t)s->n, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return bl_check_cuda(h, e, "copy snapshot");
+        }
+    }
+    if (!direct) {
+        e = cudaMemcpyAsync(h->h_result, h->d_result, sizeof(bl_result), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return bl_check_cuda(h, e, "copy result");
+    }
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "bl_evolve kernel");
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
@@ -214,6 +240,13 @@ static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_
 int bl_evolve(bl_handle *h, const bl_system *s, double time, double end_time, int64_t max_events, int first_kind,
               const bl_log *log, bl_result *out, void *stream) {
     return run_evolve(h, s, time, end_time, max_events, first_kind, log, 0, out, stream);
+}
+
+int bl_evolve_snapshot(bl_handle *h, const bl_system *s, double time, double end_time, int64_t max_events,
+                       int first_kind, const bl_log *log, bl_result *out, double *d_snap, double *host_snap,
+                       void *stream) {
+    if (!d_snap) return BL_EINVAL;
+    return run_evolve(h, s, time, end_time, max_events, first_kind, log, 0, out, stream, d_snap, host_snap);
 }
 
 int bl_next(bl_handle *h, const bl_system *s, double time, bl_result *out, void *stream) {
@@ -233,9 +266,16 @@ int bl_snapshot(bl_handle *h, const bl_system *s, double time, double *d_out, do
     if (rc) return rc;
     if (!d_out) return BL_EINVAL;
     cudaStream_t st = as_stream(stream);
-    rc = bl_launch_snapshot(h, s, time, d_out, st);
+    // page-locked host memory is written by the kernel itself (no copy operation behind it)
+    double *host_dev = nullptr;
+    if (host_out && cudaHostGetDevicePointer((void **)&host_dev, host_out, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        host_dev = nullptr;
+    }
+    rc = bl_launch_snapshot(h, s, time, nullptr, d_out, st, host_dev);
     if (rc || !host_out || s->n == 0) return rc;
-    cudaError_t e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * 8 * (size_t)s->n, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    if (!host_dev) e = cudaMemcpyAsync(host_out, d_out, sizeof(double) * 8 * (size_t)s->n, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     return bl_check_cuda(h, e, "bl_snapshot copy");
 }

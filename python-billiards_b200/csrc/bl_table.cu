@@ -142,16 +142,36 @@ __global__ void __launch_bounds__(256) bl_positions_kernel(const bl_system S, co
 
 // everything the host mirrors of a Billiard in one pass: out = [4][n][2] = balls_position (at `time`), balls_velocity,
 // balls_initial_position, balls_initial_time (both columns) -- one launch and one copy per frame of an animation loop
-__global__ void __launch_bounds__(256) bl_snapshot_kernel(const bl_system S, const double time, double *__restrict__ out) {
+// d_time != NULL: the time is read from device memory (the clock an evolve launch earlier on the stream has left)
+// out2 != NULL: a second copy, meant for page-locked host memory written over the bus (no copy operation behind the
+// kernel); res_dst != NULL: the result block of the evolve launch goes the same way
+__global__ void __launch_bounds__(256) bl_snapshot_kernel(const bl_system S, const double time_arg,
+                                                          const double *__restrict__ d_time, double *__restrict__ out,
+                                                          double *__restrict__ out2, const bl_result *__restrict__ res_src,
+                                                          bl_result *__restrict__ res_dst) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = S.n;
+    if (res_dst && blockIdx.x == 0) {
+        static_assert(sizeof(bl_result) % 8 == 0, "bl_result is copied in 8-byte words");
+        for (int w = threadIdx.x; w < (int)(sizeof(bl_result) / 8); w += blockDim.x)
+            reinterpret_cast<unsigned long long *>(res_dst)[w] = reinterpret_cast<const unsigned long long *>(res_src)[w];
+    }
     if (k >= n) return;
+    const double time = d_time ? *d_time : time_arg;
     const double t0 = S.t0[k], p0x = S.p0x[k], p0y = S.p0y[k], vx = S.vx[k], vy = S.vy[k];
     double2 *o = reinterpret_cast<double2 *>(out);
-    o[k] = make_double2(bl_advance(p0x, vx, time, t0), bl_advance(p0y, vy, time, t0));
+    const double2 pos = make_double2(bl_advance(p0x, vx, time, t0), bl_advance(p0y, vy, time, t0));
+    o[k] = pos;
     o[n + k] = make_double2(vx, vy);
     o[2 * n + k] = make_double2(p0x, p0y);
     o[3 * n + k] = make_double2(t0, t0);
+    if (out2) {
+        double2 *o2 = reinterpret_cast<double2 *>(out2);
+        o2[k] = pos;
+        o2[n + k] = make_double2(vx, vy);
+        o2[2 * n + k] = make_double2(p0x, p0y);
+        o2[3 * n + k] = make_double2(t0, t0);
+    }
 }
 
 // recompute_toi's edit detection, simulation.py:255-260
@@ -215,9 +235,10 @@ int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_row_minima_kernel");
 }
 
-int bl_launch_snapshot(bl_handle *h, const bl_system *s, double time, double *d_out, cudaStream_t st) {
+int bl_launch_snapshot(bl_handle *h, const bl_system *s, double time, const double *d_time, double *d_out, cudaStream_t st,
+                       double *out2, const bl_result *res_src, bl_result *res_dst) {
     if (s->n <= 0) return BL_OK;
-    bl_snapshot_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(*s, time, d_out);
+    bl_snapshot_kernel<<<(unsigned)((s->n + 255) / 256), 256, 0, st>>>(*s, time, d_time, d_out, out2, res_src, res_dst);
     h->launches++;
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_snapshot_kernel");
 }

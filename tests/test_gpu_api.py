@@ -449,3 +449,39 @@ def test_reference_examples_run_headless(bl, name):
         assert frames["ball_ball"] + frames["ball_obstacle"] == EXAMPLE_COUNTS[name]
     if name == "pool_first_shot":
         assert frames["ball_ball"] + frames["ball_obstacle"] > 100
+
+
+def test_evolve_snapshot_entry_point_pinned_and_pageable_host_memory(bl):
+    """bl_evolve_snapshot (include/billiards_b200.h): evolve + host mirrors in one wait.  Page-locked host memory is
+    written by the snapshot kernel directly, pageable memory through a staged copy -- same bytes, equal to what
+    bl_evolve followed by bl_snapshot gives."""
+    import ctypes
+    import torch
+    from billiards import _lib
+    cfg = workloads.hetero_gas()
+    out = []
+    for kind in ("pinned", "pageable", "separate"):
+        b = cfg.build(bl)
+        b._flush()
+        h, n = b._h(), b._n
+        s = b._system()
+        res = _lib.BlResult()
+        d_snap = torch.empty(8 * n, dtype=torch.float64, device=h.torch_device)
+        if kind == "pinned":
+            host = torch.empty(8 * n, dtype=torch.float64, pin_memory=True).numpy()
+        else:
+            host = np.empty(8 * n, dtype=np.float64)
+        host[:] = -1.0
+        hp = ctypes.c_void_p(host.ctypes.data)
+        if kind == "separate":
+            h.check(h.lib.bl_evolve(h.h, ctypes.byref(s), 0.0, 2.5, -1, _lib.BL_ANY, None, ctypes.byref(res), h.stream()))
+            h.check(h.lib.bl_snapshot(h.h, ctypes.byref(s), res.time, _lib.ptr(d_snap), hp, h.stream()))
+        else:
+            h.check(h.lib.bl_evolve_snapshot(h.h, ctypes.byref(s), 0.0, 2.5, -1, _lib.BL_ANY, None, ctypes.byref(res),
+                                             _lib.ptr(d_snap), hp, h.stream()))
+        assert res.time == 2.5 and res.n_ball_ball + res.n_ball_obstacle > 50
+        assert np.array_equal(d_snap.cpu().numpy().view(np.uint64), host.view(np.uint64))
+        out.append((host.copy(), res.n_ball_ball, res.n_ball_obstacle))
+    for other in out[1:]:
+        assert np.array_equal(out[0][0].view(np.uint64), other[0].view(np.uint64))
+        assert out[0][1:] == other[1:]
