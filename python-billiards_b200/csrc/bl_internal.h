@@ -98,6 +98,7 @@ int bl_launch_symmetrize(bl_handle *h, const bl_system *s, cudaStream_t st);
 int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_t *d_idx, cudaStream_t st);
 int bl_launch_apply_edits(bl_handle *h, const bl_system *s, double time, const double *d_pos, const double *d_vel,
                           cudaStream_t st);
+int bl_launch_result_to_host(bl_handle *h, const bl_result *src, bl_result *dst_dev, cudaStream_t st);
 int bl_launch_snapshot(bl_handle *h, const bl_system *s, double time, const double *d_time, double *d_out, cudaStream_t st,
                        double *out2 = nullptr, const bl_result *res_src = nullptr, bl_result *res_dst = nullptr);
 int bl_launch_positions(bl_handle *h, const bl_system *s, double time, double *d_pos, cudaStream_t st);

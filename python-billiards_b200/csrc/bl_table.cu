@@ -235,6 +235,18 @@ int bl_launch_row_minima(bl_handle *h, const bl_system *s, double *d_toi, int64_
     return bl_check_cuda(h, cudaGetLastError(), "launch bl_row_minima_kernel");
 }
 
+// the result block of an evolve / query launch into page-locked host memory, behind the launch on its stream (a copy
+// operation in its place costs several microseconds more before the host's wait returns)
+__global__ void bl_result_to_host_kernel(const bl_result *__restrict__ src, bl_result *__restrict__ dst) {
+    for (int w = threadIdx.x; w < (int)(sizeof(bl_result) / 8); w += blockDim.x)
+        reinterpret_cast<unsigned long long *>(dst)[w] = reinterpret_cast<const unsigned long long *>(src)[w];
+}
+
+int bl_launch_result_to_host(bl_handle *h, const bl_result *src, bl_result *dst_dev, cudaStream_t st) {
+    bl_result_to_host_kernel<<<1, 64, 0, st>>>(src, dst_dev);
+    return bl_check_cuda(h, cudaGetLastError(), "launch bl_result_to_host_kernel");
+}
+
 int bl_launch_snapshot(bl_handle *h, const bl_system *s, double time, const double *d_time, double *d_out, cudaStream_t st,
                        double *out2, const bl_result *res_src, bl_result *res_dst) {
     if (s->n <= 0) return BL_OK;
