@@ -485,3 +485,51 @@ def test_evolve_snapshot_entry_point_pinned_and_pageable_host_memory(bl):
     for other in out[1:]:
         assert np.array_equal(out[0][0].view(np.uint64), other[0].view(np.uint64))
         assert out[0][1:] == other[1:]
+
+
+def test_two_host_threads_share_one_handle(bl):
+    """One bl_handle per (device, dot mode) is shared by every Billiard of the process and ctypes drops the GIL during
+    a call: the entry points serialise on the handle's mutex (csrc/bl_internal.h: bl_entry_guard), so two threads
+    evolving their own billiards -- a gas on the grid-wide kernel (barrier counters, exchange buffers and result block
+    live in the handle) and a pool table on the lane kernel -- get exactly what they get alone."""
+    import threading
+
+    def gas_job():
+        b = workloads.dense_gas(12).build(bl)
+        out = []
+        for f in range(1, 41):
+            out.append(b.evolve(0.05 * f))
+            out.append(b.balls_position.copy())
+        return out
+
+    def pool_job():
+        b = workloads.pool().build(bl)
+        out = []
+        for f in range(1, 201):
+            out.append(b.evolve(0.5 * f))
+            out.append(b.balls_velocity.copy())
+        return out
+
+    alone = [gas_job(), pool_job()]
+    got = [None, None]
+    errors = []
+
+    def worker(slot, job):
+        try:
+            got[slot] = job()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(0, gas_job)), threading.Thread(target=worker, args=(1, pool_job))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    for a, g in zip(alone, got):
+        assert len(a) == len(g)
+        for x, y in zip(a, g):
+            if isinstance(x, tuple):
+                assert x == y
+            else:
+                assert np.array_equal(x.view(np.uint64), y.view(np.uint64))
