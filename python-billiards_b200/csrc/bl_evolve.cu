@@ -1297,8 +1297,11 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
 
 // ---------------------------------------------------------------------------------------------
 // CTA shape: Tb balls per CTA, H threads per ball ("Grid").
-static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, int *sync_mode) {
+// `m_max` (collisions per round the shared-memory layout has room for) follows from Tb, except for the largest systems
+// (more than 148 x 224 balls), where it is what is left of the shared memory after the per-ball state.
+static int pick_shape(const bl_handle *h, int n, int n_obs, int *ncta, int *tb, int *hh, int *sync_mode, int *m_max_out) {
     *hh = 1;
+    *m_max_out = 0;  // 0: pick_m_max(tb)
     if (n <= 0) { *ncta = 1; *tb = 32; *sync_mode = SYNC_CTA; return BL_OK; }
     if (n <= 64) {
         *ncta = 1; *sync_mode = SYNC_CTA;
@@ -1328,17 +1331,27 @@ static int pick_shape(const bl_handle *h, int n, int *ncta, int *tb, int *hh, in
         *ncta = (n + 63) / 64; *tb = 64; *hh = 8; *sync_mode = SYNC_GRID;
         return BL_OK;
     }
-    int t = 128;
-    while ((n + t - 1) / t > sms && t <= BL_MAX_THREADS) t += 32;
-    if (t > BL_MAX_THREADS) return BL_EUNSUPPORTED;
-    *ncta = (n + t - 1) / t; *tb = t; *sync_mode = SYNC_GRID;
-    *hh = t <= 128 ? 4 : (t <= 256 ? 2 : 1);
-    return BL_OK;
+    // large systems: the fewest balls per CTA that one CTA per SM can hold, as many threads per ball and collisions per
+    // round as its state, candidates, undo copy and parked solutions leave room for in shared memory
+    const size_t limit = h->max_smem_optin;
+    for (int t = 128; t <= BL_MAX_THREADS; t += 32) {
+        if ((n + t - 1) / t > sms) continue;
+        for (int hq = t <= 128 ? 4 : (t <= 256 ? 2 : 1); hq >= 1; hq >>= 1) {
+            for (int mm = pick_m_max(t); mm >= BL_M_MIN_LARGE; mm--) {
+                if ((size_t)make_layout(t, hq, mm, n_obs).words * 8 > limit) continue;
+                *ncta = (n + t - 1) / t; *tb = t; *hh = hq; *sync_mode = SYNC_GRID;
+                *m_max_out = mm == pick_m_max(t) ? 0 : mm;
+                return BL_OK;
+            }
+        }
+        break;  // more balls per CTA need more, not less
+    }
+    return BL_EUNSUPPORTED;
 }
 
 int bl_evolve_pick_config(const bl_handle *h, int n, int *ncta, int *threads, int *sync_mode) {
-    int tb, hh;
-    const int rc = pick_shape(h, n, ncta, &tb, &hh, sync_mode);
+    int tb, hh, mm;
+    const int rc = pick_shape(h, n, 4, ncta, &tb, &hh, sync_mode, &mm);
     *threads = tb * hh;
     return rc;
 }
@@ -1378,11 +1391,12 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st) {
     if (s->n <= BL_SMALL_MAX_BALLS && s->n_obstacles <= BL_SMALL_MAX_OBS && !h->small_kernel_off)
         return bl_launch_evolve_small(h, s, time, end_time, max_events, first_kind, log, query_only, st);
-    int ncta, tb, hh, sync_mode;
-    int rc = pick_shape(h, s->n, &ncta, &tb, &hh, &sync_mode);
+    int ncta, tb, hh, sync_mode, mm_fit;
+    int rc = pick_shape(h, s->n, s->n_obstacles, &ncta, &tb, &hh, &sync_mode, &mm_fit);
     if (rc != BL_OK)
-        return bl_set_error(h, rc, "the event kernel keeps ball state resident on chip: n=%d exceeds %d CTAs x %d "
-                            "balls", s->n, h->sm_count, BL_MAX_THREADS);
+        return bl_set_error(h, rc, "the event kernel keeps ball state resident on chip: the shared memory of %d SMs "
+                            "(%zu B each) does not hold n=%d balls with %d obstacles (limit: about %d balls)", h->sm_count,
+                            h->max_smem_optin, s->n, s->n_obstacles, h->sm_count * 448);
     Params P;
     P.s = *s;
     P.time = time; P.end_time = end_time; P.max_events = max_events; P.first_kind = first_kind;
@@ -1390,7 +1404,7 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     if (log) P.log = *log; else { P.log.cap = 0; P.log.t = nullptr; P.log.i = nullptr; P.log.j = nullptr; P.log.payload = nullptr; }
     P.result = h->d_result;
     P.Tb = tb; P.H = hh; P.ncta = ncta; P.sync_mode = sync_mode;
-    P.m_max = pick_m_max(tb);
+    P.m_max = mm_fit ? mm_fit : pick_m_max(tb);
     // Keys per round the window aims at.  The chance that a round is cut short grows like m^2 / n, the synchronisation
     // cost per collision falls like 1 / m; measured optimum on B200 (profiles/r1_target_scan.log): N = 256: 12-14,
     // 1024: 22-28, 4096: 36-40, >= 16384: 56-60, i.e. ~ 2.46 n^0.316.
@@ -1416,15 +1430,15 @@ int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_t
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset barrier");
     h->launches++;
     const bool kone = s->n_classes == 1;
-    if (tb == 128 && hh == 4) {
+    if (tb == 128 && hh == 4 && !mm_fit) {
         if (kone) return h->dot_fma ? launch_t<true, 512, 128, 4, true>(h, P, smem, st) : launch_t<false, 512, 128, 4, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 128, 4>(h, P, smem, st) : launch_t<false, 512, 128, 4>(h, P, smem, st);
     }
-    if (tb == 32 && hh == 16) {
+    if (tb == 32 && hh == 16 && !mm_fit) {
         if (kone) return h->dot_fma ? launch_t<true, 512, 32, 16, true>(h, P, smem, st) : launch_t<false, 512, 32, 16, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 32, 16>(h, P, smem, st) : launch_t<false, 512, 32, 16>(h, P, smem, st);
     }
-    if (tb == 64 && hh == 8) {
+    if (tb == 64 && hh == 8 && !mm_fit) {
         if (kone) return h->dot_fma ? launch_t<true, 512, 64, 8, true>(h, P, smem, st) : launch_t<false, 512, 64, 8, true>(h, P, smem, st);
         return h->dot_fma ? launch_t<true, 512, 64, 8>(h, P, smem, st) : launch_t<false, 512, 64, 8>(h, P, smem, st);
     }

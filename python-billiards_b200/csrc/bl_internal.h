@@ -47,6 +47,7 @@ struct bl_handle {
 #define BL_EV_CAP 256         // keys collected per round (>= number of CTAs: the exact argmin posts one per CTA)
 #define BL_SORT_CAP 64        // keys a window round sorts (two per lane of warp 0); more -> the window is halved
 #define BL_M_MAX 48           // collisions committed per round, at most
+#define BL_M_MIN_LARGE 4      // the largest systems trade collisions per round for balls per CTA, down to this many
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
 #define BL_SMALL_MAX_BALLS 32  // systems up to this size run in the one-warp kernel (bl_evolve_small.cu)
 #define BL_SMALL_MAX_OBS 32

@@ -391,6 +391,39 @@ def test_beyond_16384_balls(billiards, oracle):
     assert digests[0][2] < 30000 / 8 <= digests[1][2]
 
 
+@pytest.mark.parametrize("side,events", [(190, 4000), (256, 3000)], ids=["36100", "65536"])
+def test_largest_systems_trade_threads_and_batch_size_for_balls(billiards, side, events):
+    """Beyond 148 x 224 balls a CTA's shared memory no longer holds two helper threads per ball and full-size batches:
+    36100 balls run 256 per CTA with one thread each, 65536 balls (a 34 GB table) 448 per CTA and at most 4 collisions per
+    round.  Out of the oracle's reach, so: batched rounds vs one collision per round (the reference's schedule) must
+    give the same log and the same bits, the energy is conserved and everybody stays in the box."""
+    from billiards import _lib
+    import hashlib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+    cfg = workloads.dense_gas(side, seed=5, phi=0.4)
+    digests = []
+    for target in (0, 1):
+        h.check(h.lib.bl_set_batch_target(h.h, target))
+        try:
+            bld = build(billiards, cfg, fma)
+            _, (t, i, j) = bld.evolve_events(events, log_capacity=events)
+        finally:
+            h.check(h.lib.bl_set_batch_target(h.h, 0))
+        assert len(t) == events and np.all(np.diff(t) >= -1e-10)
+        vel, pos = bld.balls_velocity.copy(), bld.balls_position.copy()
+        digests.append((hashlib.sha256(t.tobytes() + i.tobytes() + j.tobytes()).hexdigest(), vel, pos,
+                        int(bld.last_result.prof[5])))
+        del bld
+    assert digests[0][0] == digests[1][0]
+    assert_bits_equal(digests[0][1], digests[1][1], "velocities")
+    assert_bits_equal(digests[0][2], digests[1][2], "positions")
+    assert 2 * digests[0][3] < events <= digests[1][3]  # batches really were batches; one per round really was one
+    r = float(cfg.radius[0])
+    assert abs((digests[0][1] ** 2).sum() - (cfg.vel ** 2).sum()) < 1e-9 * (cfg.vel ** 2).sum()
+    assert digests[0][2].min() >= r * (1 - 1e-9) and digests[0][2].max() <= side - r * (1 - 1e-9)
+
+
 def test_small_systems_through_the_grid_kernel(billiards, golden):
     """Systems of <= 32 balls normally run in the one-warp kernel; the grid-wide kernel must give the same bits."""
     from billiards import _lib
