@@ -1252,7 +1252,7 @@ __global__ void __launch_bounds__(MAXT, 1) bl_evolve_kernel(const __grid_constan
                 // combine the helpers' next-obstacle minima (first obstacle in list order among equal times)
                 double t_min = BL_INF, arg_min = 0.0;
                 int q_min = -1;
-                for (int g = 0; g < H; g++) {
+                for (int g = 0; g < H && g < n_obs; g++) {  // (helper g >= n_obs had no obstacle to look at)
                     const double t = as_d(obsp[(g * 3 + 0) * Tb + bl]);
                     const int qg = (int)obsp[(g * 3 + 2) * Tb + bl];
                     if (qg >= 0 && (t < t_min || (t == t_min && qg < q_min))) { t_min = t; q_min = qg; arg_min = as_d(obsp[(g * 3 + 1) * Tb + bl]); }
