@@ -361,6 +361,12 @@ def test_library_calls_on_a_non_current_device(billiards, oracle):
     bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
     assert bld.evolve(100.0) == (167, 248)
     assert torch.cuda.current_device() == 0
+    # the host mirrors: written by a kernel on cuda:1 into page-locked memory that was allocated with cuda:0 current
+    b0 = billiards.Billiard(obs, device=0, dot_fma=fma)
+    b0.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
+    assert b0.evolve(100.0) == (167, 248)
+    assert_bits_equal(bld.balls_position, b0.balls_position, "positions read back from cuda:1")
+    assert_bits_equal(bld.balls_velocity, b0.balls_velocity, "velocities read back from cuda:1")
     gas = workloads.dense_gas(20, seed=1)
     g = billiards.Billiard(workloads.make_obstacles(billiards, gas.obstacles), device=1, dot_fma=fma)
     g.add_balls(gas.pos, gas.vel, gas.radius, gas.mass)
