@@ -6,7 +6,8 @@ point particles into a single ``Billiard`` (and ``Notes.md:14`` wishes for a ``P
 * **one ball per system** (``pos`` of shape ``(S, 2)``; config S of BASELINE.json): every system is exactly "a
   ``Billiard`` with one ball" stepped with ``bounce_ball_obstacle()`` (simulation.py:504-554), one CUDA thread per
   system (``bl_ensemble_run``);
-* **n <= 32 balls per system** (``pos`` of shape ``(S, n, 2)``; e.g. 2^16 pool tables with different break shots): every
+* **n <= 224 balls per system** (``pos`` of shape ``(S, n, 2)``; e.g. 2^16 pool tables with different break shots; up to
+  32 balls a group of lanes serves a system, from 33 balls one CTA with the table in shared memory): every
   system is exactly "a ``Billiard`` with these n balls" run with ``evolve`` (simulation.py:354-438), W = 2..32 lanes of
   a warp per system with the system's time-of-impact table in shared memory (``bl_multi_run``) -- the same kernel
   that serves a single small ``Billiard``, so system s of the ensemble and a ``Billiard`` built from the same numbers
@@ -55,7 +56,7 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, m
     CUDA stream, so the copy engines work on one block while the SMs run the collision loop of another (the kernels are
     bound by instruction issue / the FP64 pipe, the copies by PCIe).  Results are what
     ``BilliardEnsemble(...).run(n_collisions, end_time)`` gives (systems are independent: the partition does not matter).
-    ``pos`` / ``vel``: ``(S, 2)`` (one ball per system) or ``(S, n, 2)`` (n <= 32 balls per system; ``radius`` and ``mass``
+    ``pos`` / ``vel``: ``(S, 2)`` (one ball per system) or ``(S, n, 2)`` (n <= 224 balls per system; ``radius`` and ``mass``
     per ball slot), ideally pinned torch CPU tensors (numpy arrays are staged through a pinned buffer first).  Returns a
     dict of numpy arrays -- ``time`` (S,), ``position`` (of the last collision for one-ball systems, at each system's
     clock otherwise), ``velocity``, ``counts`` (S,), ``stats`` -- views of pinned buffers that the next call overwrites.
@@ -120,7 +121,7 @@ def _as_f64_tensor(x):
 
 
 class BilliardEnsemble:
-    """S independent systems: the obstacles + one ball each (``pos`` (S, 2)) or n <= 32 balls each (``pos`` (S, n, 2)),
+    """S independent systems: the obstacles + one ball each (``pos`` (S, 2)) or n <= 224 balls each (``pos`` (S, n, 2)),
     all starting at time 0.
 
     Args:
@@ -174,8 +175,8 @@ class BilliardEnsemble:
         h = self._handle
         dev = h.torch_device
         S, n = self.n, self.balls_per_system
-        if not 1 <= n <= 32:
-            raise ValueError(f"multi-ball ensembles hold 1..32 balls per system, got {n} "
+        if not 1 <= n <= 224:
+            raise ValueError(f"multi-ball ensembles hold 1..224 balls per system, got {n} "
                              "(larger systems are single Billiards: the grid-wide event kernel)")
         self.balls_radius = [float(x) for x in np.broadcast_to(np.asarray(radius, dtype=np.float64), (n,))]
         self.balls_mass = [float(x) for x in np.broadcast_to(np.asarray(mass, dtype=np.float64), (n,))]

@@ -85,6 +85,7 @@ int bl_create(bl_handle **out, int device, int dot_fma) {
         const char *cm = getenv("BL_CLUSTER_MAX");
         h->cluster_max = cm ? atoi(cm) : 0;
         h->tb32_max = default_tb32_max();
+        h->cta_single_max = BL_CTA_SINGLE_MAX;
     }
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bl_check_cuda(h, e, "cudaEventCreate");
@@ -362,9 +363,9 @@ int bl_selftest_div2(bl_handle *h, uint64_t seed, int64_t n_pairs, int64_t *mism
 int bl_multi_run(bl_handle *h, const bl_multi *m, int build_tables, double end_time, int64_t max_events, void *stream) {
     if (!h || !m) return BL_EINVAL;
     bl_entry_guard g(h);
-    if (m->n < 1 || m->n > BL_SMALL_MAX_BALLS || m->n_obstacles > BL_SMALL_MAX_OBS || m->n_classes < 1)
+    if (m->n < 1 || m->n > BL_CTA_MAX_BALLS || m->n_obstacles > BL_SMALL_MAX_OBS || m->n_classes < 1)
         return bl_set_error(h, BL_EUNSUPPORTED, "bl_multi_run: systems of 1..%d balls and at most %d obstacles (n=%d, "
-                            "obstacles=%d)", BL_SMALL_MAX_BALLS, BL_SMALL_MAX_OBS, m->n, m->n_obstacles);
+                            "obstacles=%d)", BL_CTA_MAX_BALLS, BL_SMALL_MAX_OBS, m->n, m->n_obstacles);
     if (end_time != end_time) return bl_set_error(h, BL_EINVAL, "end_time is NaN");
     cudaStream_t st = as_stream(stream);
     cudaEventRecord(h->ev0, st);
@@ -412,6 +413,7 @@ int bl_set_small_kernel(bl_handle *h, int enable) {
     if (!h) return BL_EINVAL;
     h->small_kernel_off = enable ? 0 : 1;
     h->small_force_lanes = enable == 2 ? 1 : 0;
+    h->cta_single_max = enable == 3 ? BL_CTA_MAX_BALLS : BL_CTA_SINGLE_MAX;
     return BL_OK;
 }
 

@@ -1390,7 +1390,8 @@ static int launch_t(bl_handle *h, Params &P, size_t smem, cudaStream_t st) {
 
 int bl_launch_evolve(bl_handle *h, const bl_system *s, double time, double end_time, long long max_events,
                      int first_kind, const bl_log *log, int query_only, cudaStream_t st) {
-    if (s->n <= BL_SMALL_MAX_BALLS && s->n_obstacles <= BL_SMALL_MAX_OBS && !h->small_kernel_off)
+    if (s->n_obstacles <= BL_SMALL_MAX_OBS && !h->small_kernel_off &&
+        (s->n <= BL_SMALL_MAX_BALLS || s->n <= h->cta_single_max))
         return bl_launch_evolve_small(h, s, time, end_time, max_events, first_kind, log, query_only, st);
     int ncta, tb, hh, sync_mode, mm_fit;
     int rc = pick_shape(h, s->n, s->n_obstacles, &ncta, &tb, &hh, &sync_mode, &mm_fit);

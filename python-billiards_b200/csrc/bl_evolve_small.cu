@@ -456,6 +456,8 @@ int bl_launch_evolve_small(bl_handle *h, const bl_system *s, double time, double
     cudaError_t e = cudaMemsetAsync(h->d_result, 0, sizeof(bl_result), st);
     if (e != cudaSuccess) return bl_check_cuda(h, e, "memset result");
     h->launches++;
+    if (P.n > BL_SMALL_MAX_BALLS)
+        return bl_check_cuda(h, bl_launch_cta(P, h->dot_fma != 0, true, st), "launch bl_evolve_cta_kernel");
     if (P.n <= BL_TINY_MAX_BALLS && !h->small_force_lanes)
         return bl_check_cuda(h, bl_launch_tiny(P, h->dot_fma != 0, true, h->sm_count, st), "launch bl_evolve_tiny_kernel");
     e = h->dot_fma ? launch_w<true, true>(P, h->sm_count, st) : launch_w<false, true>(P, h->sm_count, st);
@@ -477,6 +479,8 @@ int bl_launch_multi(bl_handle *h, const bl_multi *m, int build_tables, double en
     P.build_tables = build_tables;
     P.sys_time = m->time; P.n_bb = m->n_ball_ball; P.n_bo = m->n_ball_obstacle; P.status = m->status;
     h->launches++;
+    if (P.n > BL_SMALL_MAX_BALLS)
+        return bl_check_cuda(h, bl_launch_cta(P, h->dot_fma != 0, false, st), "launch bl_evolve_cta_kernel (ensemble)");
     if (P.n <= BL_TINY_MAX_BALLS && !h->small_force_lanes)
         return bl_check_cuda(h, bl_launch_tiny(P, h->dot_fma != 0, false, h->sm_count, st),
                              "launch bl_evolve_tiny_kernel (ensemble)");

@@ -33,6 +33,7 @@ struct bl_handle {
     const void *window_sys;
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
     int small_kernel_off;     // bl_set_small_kernel(h, 0): systems of <= 32 balls also take the grid-wide event kernel
+    int cta_single_max;       // single systems of 33 .. this many balls take the one-CTA kernel (default BL_CTA_SINGLE_MAX: above, the grid-wide kernel is faster; bl_set_small_kernel(h, 3): all sizes up to 224)
     int small_force_lanes;    // bl_set_small_kernel(h, 2): systems of <= 4 balls take the lane-group kernel, not the one-thread kernel
     int ensemble_no_box;      // bl_set_ensemble_generic(h, 2): shaped kernel, but without the axis-aligned-box shortcut
     int ensemble_generic;     // BL_ENSEMBLE_GENERIC=1: always use the generic (list in shared memory) ensemble kernel
@@ -51,6 +52,9 @@ struct bl_handle {
 #define BL_WQ_CAP 64          // per-warp queue of pair solves that need the square root (two ballots may add 64)
 #define BL_SMALL_MAX_BALLS 32  // systems up to this size run in the one-warp kernel (bl_evolve_small.cu)
 #define BL_SMALL_MAX_OBS 32
+#define BL_CTA_MAX_WARPS 7     // systems of 33 .. 224 balls run one CTA per system, thread = ball (bl_evolve_cta.cu)
+#define BL_CTA_MAX_BALLS (32 * BL_CTA_MAX_WARPS)
+#define BL_CTA_SINGLE_MAX 80   // measured on B200 (tools/mid_bench.py): N = 36 x1.26, 64 x1.16, 100 x0.79 against the grid kernel
 #define BL_TINY_MAX_BALLS 4    // systems up to this size run one thread per system (bl_evolve_tiny.cu)
 #define BL_HL_CAP 6           // finite new values of one ball listed per round (more -> that ball scans all of them)
 #define BL_RCHUNK 256         // stale candidates repaired per pass

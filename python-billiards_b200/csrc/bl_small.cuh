@@ -43,5 +43,9 @@ struct SmallParams {
 
 }  // namespace bl_small
 
+// bl_evolve_cta.cu: one CTA per system, 33 .. BL_CTA_MAX_BALLS balls
+cudaError_t bl_launch_cta(const bl_small::SmallParams &P, bool fma, bool single, cudaStream_t st);
+size_t bl_cta_smem_bytes(int n);
+
 // bl_evolve_tiny.cu
 cudaError_t bl_launch_tiny(const bl_small::SmallParams &P, bool fma, bool single, int sm_count, cudaStream_t st);

@@ -209,16 +209,19 @@ def _small_gas(rng, n, S):
 
 
 @pytest.mark.parametrize("n,kernel", [(1, 1), (2, 1), (3, 1), (4, 1), (1, 2), (2, 2), (3, 2), (4, 2), (5, 1), (8, 1),
-                                      (9, 1), (16, 1), (17, 1), (31, 1), (32, 1)])
+                                      (9, 1), (16, 1), (17, 1), (31, 1), (32, 1), (33, 1), (47, 1), (64, 1), (100, 1),
+                                      (224, 1)])
 def test_multi_ball_ensemble_against_oracle(billiards, oracle, n, kernel):
-    """S systems x n balls -- one thread per system up to 4 balls (kernel 1) or one group of W lanes per system
-    (kernel 2 forces it for n <= 4 too): evolve(T/2) + evolve(T) + run(count) == the oracle's evolve on each system,
+    """S systems x n balls -- one thread per system up to 4 balls (kernel 1), one group of W lanes per system up to 32
+    (kernel 2 forces it for n <= 4 too), one CTA per system from 33 to 224 balls: evolve(T/2) + evolve(T) + run(count) == the oracle's evolve on each system,
     bit for bit (state, clocks, counts, the whole time-of-impact table)."""
     from billiards import _lib
     fma = _lib.probe_dot_fma()
     h = _lib.get_handle(None, fma)
     rng = np.random.default_rng(50 + n)
     S = 37 if n > 4 else 150
+    if n > 32:
+        S = 11 if n <= 100 else 4
     obstacles, pos, vel, radius, mass = _small_gas(rng, n, S)
     if n <= 4 and kernel == 1:
         obstacles = obstacles[:4]  # walls only: the one-thread kernel's two-balls-per-wall loop

@@ -42,6 +42,27 @@ LOGGED = [
 
 @pytest.mark.parametrize("name,make,kw", LOGGED, ids=[c[0] for c in LOGGED])
 def test_event_log_matches_reference(billiards, golden, name, make, kw):
+    _check_against_golden_log(billiards, golden, name, make, kw)
+
+
+MID = [c for c in LOGGED if c[0] in ("hetero_gas", "maze", "maze_wide", "collapse")]  # 60, 200, 150, 200 balls
+
+
+@pytest.mark.parametrize("name,make,kw", MID, ids=[c[0] for c in MID])
+def test_event_log_through_the_one_cta_kernel(billiards, golden, name, make, kw):
+    """Single systems of 33 .. 224 balls take the grid-wide kernel by default; the one-CTA-per-system kernel that serves
+    ensembles of such systems (csrc/bl_evolve_cta.cu) must reproduce the live reference's logs, end states, row minima
+    and whole tables just the same."""
+    from billiards import _lib
+    h = _lib.get_handle(None, bool(golden(name)["dot_fma"]))
+    h.check(h.lib.bl_set_small_kernel(h.h, 3))
+    try:
+        _check_against_golden_log(billiards, golden, name, make, kw)
+    finally:
+        h.check(h.lib.bl_set_small_kernel(h.h, 1))
+
+
+def _check_against_golden_log(billiards, golden, name, make, kw):
     g = golden(name)
     fma = bool(g["dot_fma"])
     bld = build(billiards, make(), fma)
