@@ -8,7 +8,7 @@ Workloads (BASELINE.json):
   `dense_gas_16384` (config D): ONE system of 16384 hard disks at packing fraction 0.5; a step is `--events-per-step`
          collisions of that system (state and the 2.1 GB time-of-impact table stay in HBM).  The headline of a plain
          `python bench.py` (N = 1).  The same line carries `configs` (Galperin, pool, ideal gas N = 1024: configs G, P, I),
-         `frame_loop`, `ensemble` (config S on one GPU) and `pool_ensemble` (multi-ball ensemble).
+         `frame_loop`, `ensemble` (config S on one GPU), `pool_ensemble` and `gas64_ensemble` (multi-ball ensembles).
   `sinai_ensemble` (config S): 2^20 independent Sinai billiards per GPU (`--scaling weak`, default) or in total
          (`--scaling strong`), contiguous shards, no exchange during the run, one NCCL all-reduce of the statistics
          per step; a step is 10^4 collisions of every system.  The headline whenever the process was started by
@@ -498,6 +498,33 @@ def pool_tables(n_tables, seed):
     return cfg, pos, vel
 
 
+def bench_gas_ensemble(device, fma, side=8, systems=8192, end_time=2.0, steps=3):
+    """Ensemble of mid-size systems, one CTA per system (csrc/bl_evolve_cta.cu): `systems` dense gases of side*side balls
+    with different velocity directions, every one built (table) and evolved to `end_time` in one launch."""
+    import torch
+    import billiards
+    from billiards import _lib
+    h = _lib.get_handle(device, fma)
+    cfg = workloads.dense_gas(side)
+    rng = np.random.default_rng(side)
+    pos = np.ascontiguousarray(np.broadcast_to(cfg.pos[None], (systems,) + cfg.pos.shape))
+    th = rng.uniform(0, 2 * np.pi, (systems, cfg.n))
+    vel = np.stack([np.cos(th), np.sin(th)], axis=2)
+    obstacles = workloads.make_obstacles(billiards, cfg.obstacles)
+    pos_pin, vel_pin = torch.from_numpy(pos).pin_memory(), torch.from_numpy(vel).pin_memory()
+    ms, total = 0.0, 0
+    for step in range(steps + 1):
+        ens = billiards.BilliardEnsemble(obstacles, pos_pin, vel_pin, radius=float(cfg.radius[0]), mass=1.0, device=device,
+                                         dot_fma=fma)
+        bb, bo = ens.evolve(end_time)
+        if step:  # the first one warms up
+            ms += h.last_kernel_ms()
+            total += int(bb.sum() + bo.sum())
+    return {"value": total / (ms * 1e-3), "unit": "collisions/s", "ms_per_step": ms / steps, "steps": steps,
+            "config": {"workload": "gas_ensemble", "systems": systems, "balls_per_system": cfg.n, "end_time": end_time,
+                       "kernel": "bl_evolve_cta_kernel, one CTA per system, table build included"}}
+
+
 def bench_pool_ensemble(args, device, fma, rank, world, steps, warmup):
     import torch
     import billiards
@@ -753,6 +780,7 @@ def main():
             line["ensemble"]["unit"] = "collisions/s"
             pe = bench_pool_ensemble(args, device, fma, rank, world, 3, 1)
             line["pool_ensemble"] = pe
+            line["gas64_ensemble"] = bench_gas_ensemble(device, fma)
             if not args.no_cpu_baseline:
                 line["ensemble"]["cpu_baseline"] = cpu_sinai_baseline(min(args.cpu_seconds, 5.0), fma)
                 line["pool_ensemble"]["cpu_baseline"] = cpu_pool_ensemble_baseline(fma)

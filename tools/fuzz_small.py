@@ -41,9 +41,9 @@ def main():
     fma = _lib.probe_dot_fma()
     h = _lib.get_handle(None, fma)
     for case in range(n_cases):
-        n = int(rng.choice([1, 2, 2, 3, 4, 4, 5, 7, 8, 12, 16, 16, 20, 27, 32]))
+        n = int(rng.choice([1, 2, 2, 3, 4, 4, 5, 7, 8, 12, 16, 16, 20, 27, 32, 33, 41, 64, 65, 97, 130, 224]))
         kernel = 2 if (n <= 4 and rng.random() < 0.4) else 1
-        S = int(rng.integers(5, 80))
+        S = int(rng.integers(5, 80)) if n <= 32 else int(rng.integers(2, 12))  # (from 33 balls: one CTA per system)
         obstacles, pos, vel, radius, mass = tge._small_gas(rng, n, S)
         box = float(obstacles[1][1][0])
         kind = rng.random()
