@@ -915,3 +915,61 @@ def test_pow_is_libm_not_square(billiards, oracle):
     b = build(billiards, cfg, fma)
     ref = cfg.build_oracle(oracle, dot_fma=fma)
     assert_bits_equal(np.concatenate(b.toi_table), np.concatenate(ref.toi_table))
+
+
+def test_single_system_entry_points_through_the_one_cta_kernel(billiards):
+    """Everything a single Billiard asks of its event kernel -- forced first kinds (bounce_ball_ball /
+    bounce_ball_obstacle), next-collision queries, payload logs, callbacks replayed from the log, a log that fills up,
+    count and time limits, stop and resume -- on a 49-ball and a 121-ball gas: the one-CTA kernel (default up to 80
+    balls, forced above) against the grid-wide kernel, bit for bit."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    h = _lib.get_handle(None, fma)
+
+    def session(cfg):
+        out = []
+        b = build(billiards, cfg, fma)
+        def next_plain(bld):  # (the obstacle of an obstacle hit is an object of that build: keep its arguments only)
+            nc = bld.next_collision
+            return tuple(nc[:2]) + ((nc[2][1],) if isinstance(nc[2], tuple) else (nc[2],))
+        out.append(next_plain(b))
+        out.append(b.next_ball_ball_collision)
+        out.append(b.next_ball_obstacle_collision[:2])
+        for _ in range(2):
+            b.bounce_ball_obstacle()
+            out.append((b.time, b.balls_velocity.copy()))
+            b.bounce_ball_ball()
+            out.append((b.time, b.balls_velocity.copy()))
+        c, (t, i, j, p) = b.evolve_events(300, log_capacity=300, payload=True)
+        out += [c, t, i, j, p]
+        c, (t, i, j) = b.evolve_events(10**6, end_time=b.time + 0.7, log_capacity=64)   # the log fills up first
+        out += [c, t, i, j, b.time]
+        seen = []
+        cbs = {k: (lambda t_, p_, u_, v_, o_, k=k: seen.append((k, t_, p_.tolist(), u_.tolist(), v_.tolist(),
+                                                                  int(o_) if isinstance(o_, (int, np.integer)) else type(o_).__name__)))
+               for k in (0, 5, 17, 40)}
+        out.append(b.evolve(b.time + 0.5, time_callback=lambda t_: seen.append(("t", t_)), ball_callbacks=cbs))
+        out.append(seen)
+        out.append(b.evolve(b.time + 0.25))
+        out += [b.time, b.balls_position.copy(), b.balls_velocity.copy(), np.concatenate(b.toi_table),
+                np.asarray(b._balls_toi), [int(x) for x in b._balls_idx], np.asarray(b._obstacles_toi), next_plain(b)]
+        return out
+
+    def same(x, y):
+        if isinstance(x, np.ndarray):
+            return x.shape == y.shape and np.array_equal(x.view(np.uint64) if x.dtype == np.float64 else x,
+                                                         y.view(np.uint64) if y.dtype == np.float64 else y)
+        if isinstance(x, (tuple, list)):
+            return len(x) == len(y) and all(same(a, b) for a, b in zip(x, y))
+        return x == y or (x != x and y != y)
+
+    for cfg in (workloads.dense_gas(7, seed=3), workloads.dense_gas(11, seed=4)):  # 49 and 121 balls
+        results = {}
+        for mode in (3, 0):
+            h.check(h.lib.bl_set_small_kernel(h.h, mode))
+            try:
+                results[mode] = session(cfg)
+            finally:
+                h.check(h.lib.bl_set_small_kernel(h.h, 1))
+        for q, (x, y) in enumerate(zip(results[3], results[0])):
+            assert same(x, y), f"{cfg.name}: item {q} differs between the one-CTA kernel and the grid-wide kernel"
