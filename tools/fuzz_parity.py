@@ -2,6 +2,7 @@
 """Randomised parity sweep (run on the GPU box): seeded gases of many sizes, densities, batch targets and obstacle sets,
 event log + state + table compared bit for bit with the CPU oracle.  Not part of the test suite (minutes of CPU time);
     python tools/fuzz_parity.py [n_cases] [seed]
+    FUZZ_MID=1 FUZZ_SMALL_KERNEL=3 python tools/fuzz_parity.py 60 5    # 36 ... 196 balls through the one-CTA kernel
 prints one line per case and exits non-zero on the first mismatch."""
 import os
 import sys
@@ -29,7 +30,10 @@ def main():
     fma = _lib.probe_dot_fma()
     h = _lib.get_handle(None, fma)
     for case in range(n_cases):
-        side = int(rng.choice([3, 5, 6, 9, 13, 20, 31, 33, 46, 52, 70]))
+        sides = [3, 5, 6, 9, 13, 20, 31, 33, 46, 52, 70]
+        if os.environ.get("FUZZ_MID"):  # 33 ... 224 balls only: the one-CTA kernel (with FUZZ_SMALL_KERNEL=3: at every size)
+            sides = [6, 7, 8, 9, 10, 11, 12, 13, 14]
+        side = int(rng.choice(sides))
         phi = float(rng.choice([0.05, 0.2, 0.4, 0.55, 0.7]))
         target = int(rng.choice([0, 0, 1, 2, 3, 7, 20, 40]))
         hetero = side <= 46 and rng.random() < 0.4
@@ -53,6 +57,7 @@ def main():
         ref.evolve(INF, max_events=n_events)
         rt, ri, rj = ref.log()
         h.check(h.lib.bl_set_batch_target(h.h, target))
+        h.check(h.lib.bl_set_small_kernel(h.h, int(os.environ.get("FUZZ_SMALL_KERNEL", "1"))))
         try:
             bld = billiards.Billiard(workloads.make_obstacles(billiards, cfg.obstacles), dot_fma=fma)
             bld.add_balls(cfg.pos, cfg.vel, cfg.radius, cfg.mass)
@@ -67,6 +72,7 @@ def main():
                     break
         finally:
             h.check(h.lib.bl_set_batch_target(h.h, 0))
+            h.check(h.lib.bl_set_small_kernel(h.h, 1))
         t, i, j = np.concatenate(ts), np.concatenate(ii), np.concatenate(jj)
         ok = (len(t) == len(rt) and np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(bits(t), bits(rt))
               and np.array_equal(bits(bld.balls_velocity), bits(ref.state()["v"]))
