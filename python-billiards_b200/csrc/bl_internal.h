@@ -32,7 +32,7 @@ struct bl_handle {
     int window_n;
     const void *window_sys;
     int target_override;      // > 0: collisions per round to aim at (bl_set_batch_target)
-    int small_kernel_off;     // bl_set_small_kernel(h, 0): systems of <= 32 balls also take the grid-wide event kernel
+    int small_kernel_off;     // bl_set_small_kernel(h, 0): every system takes the grid-wide event kernel (default: <= 32 balls lane groups, <= 80 one CTA)
     int cta_single_max;       // single systems of 33 .. this many balls take the one-CTA kernel (default BL_CTA_SINGLE_MAX: above, the grid-wide kernel is faster; bl_set_small_kernel(h, 3): all sizes up to 224)
     int small_force_lanes;    // bl_set_small_kernel(h, 2): systems of <= 4 balls take the lane-group kernel, not the one-thread kernel
     int ensemble_no_box;      // bl_set_ensemble_generic(h, 2): shaped kernel, but without the axis-aligned-box shortcut

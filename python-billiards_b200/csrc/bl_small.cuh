@@ -1,4 +1,4 @@
-// bl_small.cuh -- launch parameters shared by the two kernels for systems of at most 32 balls:
+// bl_small.cuh -- launch parameters shared by the kernels for small and mid-size systems (bl_evolve_cta.cu: 33 ... 224 balls) and, at most 32 balls:
 // bl_evolve_small.cu (one group of W lanes per system) and bl_evolve_tiny.cu (one thread per system, n <= 4).
 #pragma once
 #include "bl_arith.cuh"

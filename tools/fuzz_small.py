@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Randomised parity sweep of the small-system kernels and the ensemble front ends (run on the GPU box):
-  * multi-ball ensembles of 1 ... 32 balls (one thread per system, lane groups, and the lane groups forced for <= 4
+  * multi-ball ensembles of 1 ... 224 balls (one thread per system, lane groups, one CTA per system from 33 balls, and the lane groups forced for <= 4
     balls), random radii / masses / obstacle sets (walls, a disk, sometimes a line segment), stop / resume in random
     places, against the CPU oracle run per system: clocks, counts, state and the whole time-of-impact table;
   * one-ball ensembles on the randomised geometries of tests/test_gpu_ensembles.py with fresh seeds.
