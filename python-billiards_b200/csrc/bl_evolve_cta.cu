@@ -62,7 +62,7 @@ __host__ __device__ inline CtaLayout cta_layout(int n) {
 // MAXW: warps per CTA the build is for.  Ensembles of the smaller systems are bound by how many CTAs an SM holds (each
 // one a chain of ~1000-cycle steps), so the 2- and 4-warp builds trade registers for residency.
 template <bool FMA, bool SINGLE, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, (SINGLE || MAXW > 4) ? 1 : (MAXW == 2 ? 10 : 5))
+__global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAXW > 4) ? 1 : (MAXW == 2 ? 10 : 5))
     bl_evolve_cta_kernel(const __grid_constant__ SmallParams P) {
     extern __shared__ double smem[];
     __shared__ bl_obstacle s_obs[BL_SMALL_MAX_OBS];
@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(32 * MAXW, (SINGLE || MAXW > 4) ? 1 : (MAXW ==
     int *const s_oidx = reinterpret_cast<int *>(smem + L.oidx), *const s_cj = reinterpret_cast<int *>(smem + L.cj);
     int *const s_list = reinterpret_cast<int *>(smem + L.list), *const s_misc = reinterpret_cast<int *>(smem + L.misc);
     const unsigned FULL = 0xffffffffu;
+    // the warp that solves the (ball, obstacle) pairs of the colliding balls: for a single system an extra warp without
+    // balls, so that these solves run beside the pair solves of the others instead of after warp 0's (1.2 k of ~5.5 k
+    // cycles per collision); in ensembles warp 0 (the SM is kept busy by other CTAs, an extra warp would only redo the resolve)
+    const int ow = SINGLE ? nw - 1 : 0;
 
     for (int q = li; q < n_obs; q += blockDim.x) s_obs[q] = P.obstacles[q];
     const long long sys = SINGLE ? 0 : (long long)blockIdx.x;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(32 * MAXW, (SINGLE || MAXW > 4) ? 1 : (MAXW ==
         // the obstacles (l >> 1), (l >> 1) + 16, ... for ball a (even lanes) or b (odd lanes); the partial minima are
         // combined by a butterfly over the lanes of equal parity -- smaller time, then smaller list index, which is the
         // reference's strict < in list order ----
-        if (warp == 0) {
+        if (warp == ow) {
             const int which = lane & 1;
             const int tball = which ? b : a;
             const double tx = which ? bx : ax, ty = which ? by : ay, tvx = which ? bvx : avx, tvy = which ? bvy : avy;
@@ -438,7 +442,7 @@ cudaError_t launch_cta_w(const SmallParams &P, cudaStream_t st) {
     auto kern = bl_evolve_cta_kernel<FMA, SINGLE, MAXW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const unsigned threads = (unsigned)(((P.n + 31) / 32) * 32);
+    const unsigned threads = (unsigned)(((P.n + 31) / 32) * 32) + (SINGLE ? 32u : 0u);  // (single: + the obstacle warp)
     kern<<<SINGLE ? 1u : (unsigned)P.n_sys, threads, smem, st>>>(P);
     return cudaGetLastError();
 }

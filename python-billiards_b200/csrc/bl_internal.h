@@ -54,7 +54,7 @@ struct bl_handle {
 #define BL_SMALL_MAX_OBS 32
 #define BL_CTA_MAX_WARPS 7     // systems of 33 .. 224 balls run one CTA per system, thread = ball (bl_evolve_cta.cu)
 #define BL_CTA_MAX_BALLS (32 * BL_CTA_MAX_WARPS)
-#define BL_CTA_SINGLE_MAX 80   // measured on B200 (tools/mid_bench.py): N = 36 x1.26, 64 x1.16, 100 x0.79 against the grid kernel
+#define BL_CTA_SINGLE_MAX 80   // measured on B200 (tools/mid_bench.py): N = 36 x1.57, 64 x1.44, 100 x0.85 against the grid kernel
 #define BL_TINY_MAX_BALLS 4    // systems up to this size run one thread per system (bl_evolve_tiny.cu)
 #define BL_HL_CAP 6           // finite new values of one ball listed per round (more -> that ball scans all of them)
 #define BL_RCHUNK 256         // stale candidates repaired per pass

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Systems of 33 ... 224 balls: the one-CTA kernel (bl_evolve_cta.cu) against the grid-wide event kernel on the same
-box, same inputs (bl_set_small_kernel(h, 3) sends these sizes through the grid kernel); logs must agree bit for bit."""
+box, same inputs (bl_set_small_kernel(h, 0) sends every size through the grid kernel, (h, 3) every size up to 224 balls through the one-CTA kernel); logs must agree bit for bit."""
 import os
 import sys
 
@@ -20,7 +20,7 @@ cases = [(f"dense gas {s * s}", workloads.dense_gas(s)) for s in (6, 8, 10, 12, 
 cases += [("collapse 200", workloads.collapse()), ("maze 200", workloads.maze()), ("hetero", workloads.hetero_gas())]
 for name, cfg in cases:
     out = {}
-    for mode, label in ((3, "cta"), (1, "grid")):
+    for mode, label in ((3, "cta"), (0, "grid")):
         h.check(h.lib.bl_set_small_kernel(h.h, mode))
         best = None
         for rep in range(2):
