@@ -347,6 +347,20 @@ def test_run_from_host_matches_the_resident_path(billiards):
     assert_bits_equal(out["position"], whole.balls_position)
     assert out["counts"].tolist() == whole.counts.tolist()
     assert out["stats"].tolist() == whole.gather_stats().tolist()
+    # systems of 49 balls: one CTA per system
+    gas = workloads.dense_gas(7, seed=2)
+    S = 23
+    th = rng.uniform(0, 2 * pi, (S, gas.n))
+    gpos = np.repeat(gas.pos[None], S, axis=0)
+    gvel = np.stack([np.cos(th), np.sin(th)], axis=2)
+    gobs = workloads.make_obstacles(billiards, gas.obstacles)
+    whole = billiards.BilliardEnsemble(gobs, gpos, gvel, radius=float(gas.radius[0]), mass=1.0, dot_fma=fma)
+    whole.run(-1, end_time=1.5)
+    out = run_from_host(gobs, gpos, gvel, -1, end_time=1.5, radius=float(gas.radius[0]), mass=1.0, dot_fma=fma, chunks=3)
+    assert_bits_equal(out["time"], whole.time)
+    assert_bits_equal(out["velocity"], whole.balls_velocity)
+    assert_bits_equal(out["position"], whole.balls_position)
+    assert out["counts"].tolist() == whole.counts.tolist() and int(out["stats"][0]) > 1000
 
 
 def test_library_calls_on_a_non_current_device(billiards, oracle):
