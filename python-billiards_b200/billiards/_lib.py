@@ -51,7 +51,7 @@ class BlResult(ctypes.Structure):
 
 class BlMulti(ctypes.Structure):
     _fields_ = [("n_sys", ctypes.c_int64), ("n", ctypes.c_int32), ("n_classes", ctypes.c_int32),
-                ("n_obstacles", ctypes.c_int32), ("pad", ctypes.c_int32),
+                ("n_obstacles", ctypes.c_int32), ("per_system", ctypes.c_int32),
                 ("p0x", c_void), ("p0y", c_void), ("vx", c_void), ("vy", c_void), ("t0", c_void),
                 ("radius", c_void), ("mass", c_void), ("rclass", c_void), ("rsum2", c_void), ("rsum2_obs", c_void),
                 ("obstacles", c_void), ("toi", c_void), ("obs_t", c_void), ("obs_arg", c_void), ("obs_idx", c_void),

@@ -56,7 +56,7 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, m
     CUDA stream, so the copy engines work on one block while the SMs run the collision loop of another (the kernels are
     bound by instruction issue / the FP64 pipe, the copies by PCIe).  Results are what
     ``BilliardEnsemble(...).run(n_collisions, end_time)`` gives (systems are independent: the partition does not matter).
-    ``pos`` / ``vel``: ``(S, 2)`` (one ball per system) or ``(S, n, 2)`` (n <= 224 balls per system; ``radius`` and ``mass``
+    ``pos`` / ``vel``: ``(S, 2)`` (one ball per system) or ``(S, n, 2)`` (n <= 224 balls per system; ``radius`` and ``mass`` of shape (S, n) give every system its own; otherwise ``radius`` and ``mass``
     per ball slot), ideally pinned torch CPU tensors (numpy arrays are staged through a pinned buffer first).  Returns a
     dict of numpy arrays -- ``time`` (S,), ``position`` (of the last collision for one-ball systems, at each system's
     clock otherwise), ``velocity``, ``counts`` (S,), ``stats`` -- views of pinned buffers that the next call overwrites.
@@ -86,7 +86,9 @@ def run_from_host(obstacles, pos, vel, n_collisions, end_time=INF, radius=0.0, m
         st = streams[c]
         st.wait_stream(start)
         with torch.cuda.stream(st):
-            ens = BilliardEnsemble(obstacles, pos_t[lo:hi], vel_t[lo:hi], radius=radius, mass=mass, device=dev.index,
+            r_c = radius[lo:hi] if np.ndim(radius) == 2 else radius   # (per-system radii / masses follow their systems)
+            m_c = mass[lo:hi] if np.ndim(mass) == 2 else mass
+            ens = BilliardEnsemble(obstacles, pos_t[lo:hi], vel_t[lo:hi], radius=r_c, mass=m_c, device=dev.index,
                                    dot_fma=h.dot_fma, count_hits=count_hits)
             ens.run(n_collisions, end_time, sync=False)
             if multi:
@@ -178,8 +180,12 @@ class BilliardEnsemble:
         if not 1 <= n <= 224:
             raise ValueError(f"multi-ball ensembles hold 1..224 balls per system, got {n} "
                              "(larger systems are single Billiards: the grid-wide event kernel)")
-        self.balls_radius = [float(x) for x in np.broadcast_to(np.asarray(radius, dtype=np.float64), (n,))]
-        self.balls_mass = [float(x) for x in np.broadcast_to(np.asarray(mass, dtype=np.float64), (n,))]
+        r_in, m_in = np.asarray(radius, dtype=np.float64), np.asarray(mass, dtype=np.float64)
+        self._per_system = r_in.ndim == 2 or m_in.ndim == 2
+        if self._per_system:
+            return self._init_multi_per_system(pos_t, vel_t, np.broadcast_to(r_in, (S, n)), np.broadcast_to(m_in, (S, n)))
+        self.balls_radius = [float(x) for x in np.broadcast_to(r_in, (n,))]
+        self.balls_mass = [float(x) for x in np.broadcast_to(m_in, (n,))]
         classes, class_radii = {}, []
         for r in self.balls_radius:
             if r not in classes:
@@ -199,6 +205,49 @@ class BilliardEnsemble:
         d["radius"] = torch.tensor(self.balls_radius, dtype=torch.float64, device=dev)
         d["mass"] = torch.tensor(self.balls_mass, dtype=torch.float64, device=dev)
         d["rclass"] = torch.tensor([classes[r] for r in self.balls_radius], dtype=torch.int32, device=dev)
+        self._n_classes = len(class_radii)
+        self._alloc_multi_state(d, pos_t, vel_t)
+
+    def _init_multi_per_system(self, pos_t, vel_t, radius, mass):
+        """Every system its own radii and masses (``radius`` / ``mass`` of shape (S, n)): e.g. Galperin's billiard at many
+        mass ratios at once.  Radius classes are per system and per ball slot (K = n); the (r_a + r_b)**2 tables come from
+        the host's libm pow() system by system, like ``float ** 2`` in physics.py:52."""
+        import torch
+        dev = self._handle.torch_device
+        S, n = self.n, self.balls_per_system
+        self.balls_radius = np.array(radius, dtype=np.float64, order="C")   # (S, n), own writable copies
+        self.balls_mass = np.array(mass, dtype=np.float64, order="C")
+        disk_r = [float(o.radius) if rec.kind == _lib.BL_OBS_DISK else 0.0
+                  for o, rec in zip(self.obstacles, self._records)]
+        n_obs = len(self.obstacles)
+        rs = np.empty((S, n, n), dtype=np.float64)
+        rs_obs = np.zeros((S, max(n_obs, 1), n), dtype=np.float64)
+        cache = {}
+        for sys_ in range(S):
+            key = self.balls_radius[sys_].tobytes()
+            if key not in cache:
+                a, b = _lib.pow2_table(self.balls_radius[sys_], disk_r)
+                for q, rec in enumerate(self._records):
+                    if rec.kind == _lib.BL_OBS_WALL:
+                        b[q, :] = 0.0
+                cache[key] = (a, b)
+            rs[sys_] = cache[key][0]
+            if n_obs:
+                rs_obs[sys_, :n_obs] = cache[key][1]
+        d = {}
+        d["rsum2"] = torch.from_numpy(rs).to(dev)
+        d["rsum2_obs"] = torch.from_numpy(np.ascontiguousarray(rs_obs[:, :max(n_obs, 1)]).reshape(-1)).to(dev)
+        d["obstacles"] = torch.from_numpy(np.frombuffer(bytes(self._rec_array), dtype=np.uint8).copy()).to(dev)
+        d["radius"] = torch.from_numpy(self.balls_radius).to(dev)
+        d["mass"] = torch.from_numpy(self.balls_mass).to(dev)
+        d["rclass"] = torch.arange(n, dtype=torch.int32, device=dev).repeat(S, 1).contiguous()
+        self._n_classes = n
+        self._alloc_multi_state(d, pos_t, vel_t)
+
+    def _alloc_multi_state(self, d, pos_t, vel_t):
+        import torch
+        dev = self._handle.torch_device
+        S, n = self.n, self.balls_per_system
         # state of record, SoA over (system, ball): one H2D copy each for pos and vel, de-interleaved on the device
         p = pos_t.to(dev, non_blocking=True)
         v = vel_t.to(dev, non_blocking=True)
@@ -214,13 +263,13 @@ class BilliardEnsemble:
         d["n_ball_obstacle"] = torch.zeros(S, dtype=torch.int64, device=dev)
         d["status"] = torch.zeros(S, dtype=torch.int32, device=dev)
         self._dev = d
-        self._n_classes = len(class_radii)
         self._fresh = True  # tables not built yet: the first run solves every pair at time 0, like add_ball
         self._hits = None
 
     def _multi_struct(self):
         m = _lib.BlMulti()
         m.n_sys, m.n, m.n_classes, m.n_obstacles = self.n, self.balls_per_system, self._n_classes, len(self.obstacles)
+        m.per_system = 1 if self._per_system else 0
         for name in ("p0x", "p0y", "vx", "vy", "t0", "radius", "mass", "rclass", "rsum2", "rsum2_obs", "obstacles",
                      "toi", "obs_t", "obs_arg", "obs_idx", "time", "n_ball_ball", "n_ball_obstacle", "status"):
             setattr(m, name, self._dev[name].data_ptr())

@@ -86,18 +86,22 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
     const long long sys = SINGLE ? 0 : (long long)blockIdx.x;
     const bool own = li < n;
     const long long sb = sys * n;
+    // my system's composition (shared by all systems unless the strides say otherwise)
+    const double *const c_mass = P.mass + sys * P.ball_stride, *const c_radius = P.radius + sys * P.ball_stride;
+    const int32_t *const c_rclass = P.rclass + sys * P.ball_stride;
+    const double *const c_rsum2 = P.rsum2 + sys * P.rs_stride, *const c_rsum2_obs = P.rsum2_obs + sys * P.rso_stride;
 
     double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0, radius = 0, oarg = 0, ot = BL_INF;
     int rc = 0, oidx = -1;
     double now = SINGLE ? P.time : P.sys_time[sys];
     if (own) {
         p0x = P.p0x[sb + li]; p0y = P.p0y[sb + li]; vx = P.vx[sb + li]; vy = P.vy[sb + li]; t0 = P.t0[sb + li];
-        radius = P.radius[li]; rc = P.rclass[li];
+        radius = c_radius[li]; rc = c_rclass[li];
         s_p0x[li] = p0x; s_p0y[li] = p0y; s_vx[li] = vx; s_vy[li] = vy; s_t0[li] = t0;
     }
     if (li == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = -1; s_misc[3] = -1; }
-    const double *const rs_row = P.rsum2 + (size_t)rc * K;  // (r_me + r_x)**2 by the class of x
-    const double rs_one = P.rsum2[0];
+    const double *const rs_row = c_rsum2 + (size_t)rc * K;  // (r_me + r_x)**2 by the class of x
+    const double rs_one = c_rsum2[0];
     __syncthreads();
     if (!SINGLE && P.build_tables) {
         // add_ball, row by row at the current time (simulation.py:176-209): every pair solved from the positions of
@@ -106,10 +110,10 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             const double px = bl_advance(p0x, vx, now, t0), py = bl_advance(p0y, vy, now, t0);
             for (int j = 0; j < li; j++) {
                 const double jx = bl_advance(s_p0x[j], s_vx[j], now, s_t0[j]), jy = bl_advance(s_p0y[j], s_vy[j], now, s_t0[j]);
-                const double rs = K == 1 ? rs_one : rs_row[P.rclass[j]];
+                const double rs = K == 1 ? rs_one : rs_row[c_rclass[j]];
                 tri[tri_at(li, j)] = bl_add(now, bl_toi_ball_ball<FMA>(px, py, vx, vy, jx, jy, s_vx[j], s_vy[j], rs));
             }
-            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc, px, py, vx, vy, radius, now, ot, oidx, oarg);
+            bl_next_obstacle<FMA>(s_obs, n_obs, c_rsum2_obs, K, rc, px, py, vx, vy, radius, now, ot, oidx, oarg);
         }
     } else {
         if (own) { ot = P.obs_t[sb + li]; oarg = P.obs_arg[sb + li]; oidx = P.obs_idx[sb + li]; }
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             // ---- resolve, redundantly in every thread, from the mirrored states ----
             const double a0x = s_p0x[a], a0y = s_p0y[a], a_t0 = s_t0[a];
             a_vx = s_vx[a]; a_vy = s_vy[a];
-            rca = P.rclass[a];
+            rca = c_rclass[a];
             ax = bl_advance(a0x, a_vx, t, a_t0); ay = bl_advance(a0y, a_vy, t, a_t0);
             int st;
             if (b < 0) {
@@ -218,9 +222,9 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             } else {
                 const double b0x = s_p0x[b], b0y = s_p0y[b], b_t0 = s_t0[b];
                 b_vx = s_vx[b]; b_vy = s_vy[b];
-                rcb = P.rclass[b];
+                rcb = c_rclass[b];
                 bx = bl_advance(b0x, b_vx, t, b_t0); by = bl_advance(b0y, b_vy, t, b_t0);
-                double m1 = P.mass[a], m2 = P.mass[b];
+                double m1 = c_mass[a], m2 = c_mass[b];
                 bl_remap_masses(m1, m2);
                 avx = a_vx; avy = a_vy; bvx = b_vx; bvy = b_vy;
                 st = bl_elastic<FMA>(ax, ay, a_vx, a_vy, m1, bx, by, b_vx, b_vy, m2, avx, avy, bvx, bvy);
@@ -345,10 +349,10 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             double omin = BL_INF, oam = 0.0;
             int oq = -1;
             if (tball >= 0) {
-                const double tradius = P.radius[tball];
+                const double tradius = c_radius[tball];
                 for (int q = lane >> 1; q < n_obs; q += 16) {
                     double arg;
-                    const double rs = s_obs[q].kind != BL_OBS_WALL ? P.rsum2_obs[(size_t)q * K + trc] : 0.0;
+                    const double rs = s_obs[q].kind != BL_OBS_WALL ? c_rsum2_obs[(size_t)q * K + trc] : 0.0;
                     const double tq = bl_obstacle_toi<FMA>(s_obs[q], tx, ty, tvx, tvy, tradius, rs, arg);
                     if (tq < omin) { omin = tq; oq = q; oam = arg; }
                 }

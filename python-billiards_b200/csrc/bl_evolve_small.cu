@@ -105,16 +105,20 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
     if (sys >= P.n_sys) return;  // whole groups leave together: every later sync names the group's lanes only
     const bool own = li < n;
     const long long sb = sys * n;  // first ball of my system
+    // my system's composition (shared by all systems unless the strides say otherwise)
+    const double *const c_mass = P.mass + sys * P.ball_stride, *const c_radius = P.radius + sys * P.ball_stride;
+    const int32_t *const c_rclass = P.rclass + sys * P.ball_stride;
+    const double *const c_rsum2 = P.rsum2 + sys * P.rs_stride, *const c_rsum2_obs = P.rsum2_obs + sys * P.rso_stride;
 
     double p0x = 0, p0y = 0, vx = 0, vy = 0, t0 = 0, mass = 0, radius = 0, oarg = 0, ot = BL_INF;
     int rc = 0, oidx = -1;
     double now = SINGLE ? P.time : P.sys_time[sys];
     if (own) {
         p0x = P.p0x[sb + li]; p0y = P.p0y[sb + li]; vx = P.vx[sb + li]; vy = P.vy[sb + li]; t0 = P.t0[sb + li];
-        mass = P.mass[li]; radius = P.radius[li]; rc = P.rclass[li];
+        mass = c_mass[li]; radius = c_radius[li]; rc = c_rclass[li];
     }
-    const double *const rs_row = P.rsum2 + (size_t)rc * K;  // (r_me + r_x)**2 by the class of x
-    const double rs_one = P.rsum2[0];
+    const double *const rs_row = c_rsum2 + (size_t)rc * K;  // (r_me + r_x)**2 by the class of x
+    const double rs_one = c_rsum2[0];
     if (!SINGLE && P.build_tables) {
         // add_ball, row by row at the current time (simulation.py:176-209): every pair solved from the positions of
         // `now`; the solve is bit-symmetric in the two balls, so lane i fills its own row
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             Trow[j] = v;
         }
         if (own) {
-            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc, px, py, vx, vy, radius, now, ot, oidx, oarg);
+            bl_next_obstacle<FMA>(s_obs, n_obs, c_rsum2_obs, K, rc, px, py, vx, vy, radius, now, ot, oidx, oarg);
         }
     } else {
         if (own) {
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 32 * BL_SMALL_WARPS, SINGLE ? 1 
             if (tball >= 0) {
                 for (int q = li >> 1; q < n_obs_r; q += (W > 2 ? W / 2 : 1)) {
                     double arg;
-                    const double rs = s_obs[q].kind != BL_OBS_WALL ? P.rsum2_obs[(size_t)q * K + trc] : 0.0;
+                    const double rs = s_obs[q].kind != BL_OBS_WALL ? c_rsum2_obs[(size_t)q * K + trc] : 0.0;
                     const double tq = bl_obstacle_toi<FMA>(s_obs[q], tx, ty, tvx, tvy, tradius, rs, arg);
                     if (tq < omin) { omin = tq; oq = q; oam = arg; }
                 }
@@ -478,6 +482,10 @@ int bl_launch_multi(bl_handle *h, const bl_multi *m, int build_tables, double en
     P.end_time = end_time; P.max_events = max_events;
     P.build_tables = build_tables;
     P.sys_time = m->time; P.n_bb = m->n_ball_ball; P.n_bo = m->n_ball_obstacle; P.status = m->status;
+    if (m->per_system) {
+        P.ball_stride = m->n; P.rs_stride = (long long)m->n_classes * m->n_classes;
+        P.rso_stride = (long long)m->n_obstacles * m->n_classes;
+    }
     h->launches++;
     if (P.n > BL_SMALL_MAX_BALLS)
         return bl_check_cuda(h, bl_launch_cta(P, h->dot_fma != 0, false, st), "launch bl_evolve_cta_kernel (ensemble)");

@@ -87,6 +87,10 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(co
     const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= P.n_sys) return;
     const long long sb = sys * n;
+    // my system's composition (shared by all systems unless the strides say otherwise)
+    const double *const c_mass = P.mass + sys * P.ball_stride, *const c_radius = P.radius + sys * P.ball_stride;
+    const int32_t *const c_rclass = P.rclass + sys * P.ball_stride;
+    const double *const c_rsum2 = P.rsum2 + sys * P.rs_stride, *const c_rsum2_obs = P.rsum2_obs + sys * P.rso_stride;
 
     double p0x[N], p0y[N], vx[N], vy[N], t0[N], mass[N], radius[N], ot[N], oarg[N];
     int rc[N], oidx[N];
@@ -98,14 +102,14 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(co
         const bool own = k < n;
         p0x[k] = own ? P.p0x[sb + k] : 0.0; p0y[k] = own ? P.p0y[sb + k] : 0.0;
         vx[k] = own ? P.vx[sb + k] : 0.0; vy[k] = own ? P.vy[sb + k] : 0.0; t0[k] = own ? P.t0[sb + k] : 0.0;
-        mass[k] = own ? P.mass[k] : 1.0; radius[k] = own ? P.radius[k] : 0.0; rc[k] = own ? P.rclass[k] : 0;
+        mass[k] = own ? c_mass[k] : 1.0; radius[k] = own ? c_radius[k] : 0.0; rc[k] = own ? c_rclass[k] : 0;
         ot[k] = BL_INF; oarg[k] = 0.0; oidx[k] = -1;
     }
 #pragma unroll
     for (int hi = 1; hi < N; hi++)
 #pragma unroll
         for (int lo = 0; lo < hi; lo++) {
-            rs[lo][hi] = P.rsum2[(size_t)rc[lo] * K + rc[hi]];
+            rs[lo][hi] = c_rsum2[(size_t)rc[lo] * K + rc[hi]];
             T[lo][hi] = BL_INF;
         }
     if (!SINGLE && P.build_tables) {
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(co
 #pragma unroll
         for (int k = 0; k < N; k++)
             if (k < n)
-                bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, rc[k], px[k], py[k], vx[k], vy[k], radius[k], now,
+                bl_next_obstacle<FMA>(s_obs, n_obs, c_rsum2_obs, K, rc[k], px[k], py[k], vx[k], vy[k], radius[k], now,
                                       ot[k], oidx[k], oarg[k]);
     } else {
         const double *tab = P.toi + sys * P.toi_sys_stride;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_tiny_kernel(co
             const int kb = b >= 0 ? b : a;
             double o1, o2, g1, g2;
             int i1, i2;
-            next_obstacle_pair<FMA>(s_obs, n_obs, walls_only, P.rsum2_obs, K, t, b >= 0,  //
+            next_obstacle_pair<FMA>(s_obs, n_obs, walls_only, c_rsum2_obs, K, t, b >= 0,  //
                                     pick(rc, a), ax, ay, avx, avy, pick(radius, a), o1, i1, g1,  //
                                     pick(rc, kb), bx, by, bvx, bvy, pick(radius, kb), o2, i2, g2);
 #pragma unroll
@@ -473,6 +477,10 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_pair_kernel(co
     const long long sys = SINGLE ? (long long)threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (sys >= P.n_sys) return;
     const long long sb = sys * n;
+    // my system's composition (shared by all systems unless the strides say otherwise)
+    const double *const c_mass = P.mass + sys * P.ball_stride, *const c_radius = P.radius + sys * P.ball_stride;
+    const int32_t *const c_rclass = P.rclass + sys * P.ball_stride;
+    const double *const c_rsum2 = P.rsum2 + sys * P.rs_stride, *const c_rsum2_obs = P.rsum2_obs + sys * P.rso_stride;
     bool two = n == 2;
     {
         int tw = two ? 1 : 0;
@@ -480,7 +488,7 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_pair_kernel(co
         two = tw != 0;
     }
     Obstacles O;
-    O.s_obs = s_obs; O.rsum2_obs = P.rsum2_obs; O.n_obs = n_obs; O.K = K; O.walls_only = s_walls_only != 0;
+    O.s_obs = s_obs; O.rsum2_obs = c_rsum2_obs; O.n_obs = n_obs; O.K = K; O.walls_only = s_walls_only != 0;
     {
         // loop-invariant flags as opaque register values: left to itself the compiler re-derives them from the
         // constant bank inside the loop (load + compare + branch, ~20 cycles of latency each time, several per collision)
@@ -495,15 +503,15 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_pair_kernel(co
 
     Ball b0, b1;
     b0.p0x = P.p0x[sb]; b0.p0y = P.p0y[sb]; b0.vx = P.vx[sb]; b0.vy = P.vy[sb]; b0.t0 = P.t0[sb];
-    b0.mass = P.mass[0]; b0.radius = P.radius[0]; b0.rc = P.rclass[0];
+    b0.mass = c_mass[0]; b0.radius = c_radius[0]; b0.rc = c_rclass[0];
     b0.ot = BL_INF; b0.oarg = 0.0; b0.oidx = -1;
     b1 = b0;
     b1.p0x = 0.0; b1.p0y = 0.0; b1.vx = 0.0; b1.vy = 0.0; b1.t0 = 0.0; b1.mass = 1.0; b1.radius = 0.0; b1.rc = 0;
     if (two) {
         b1.p0x = P.p0x[sb + 1]; b1.p0y = P.p0y[sb + 1]; b1.vx = P.vx[sb + 1]; b1.vy = P.vy[sb + 1]; b1.t0 = P.t0[sb + 1];
-        b1.mass = P.mass[1]; b1.radius = P.radius[1]; b1.rc = P.rclass[1];
+        b1.mass = c_mass[1]; b1.radius = c_radius[1]; b1.rc = c_rclass[1];
     }
-    const double rs01 = P.rsum2[(size_t)b0.rc * K + b1.rc];
+    const double rs01 = c_rsum2[(size_t)b0.rc * K + b1.rc];
     double m1r = b0.mass, m2r = b1.mass;  // simulation.py:579-582, the same for every collision of the pair
     bl_remap_masses(m1r, m2r);
     double T01 = BL_INF;
@@ -512,11 +520,11 @@ __global__ void __launch_bounds__(SINGLE ? 32 : 128, 1) bl_evolve_pair_kernel(co
     if (!SINGLE && P.build_tables) {
         // add_ball, row by row at the current time (simulation.py:176-209)
         const double x0 = bl_advance(b0.p0x, b0.vx, now, b0.t0), y0 = bl_advance(b0.p0y, b0.vy, now, b0.t0);
-        bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, b0.rc, x0, y0, b0.vx, b0.vy, b0.radius, now, b0.ot, b0.oidx, b0.oarg);
+        bl_next_obstacle<FMA>(s_obs, n_obs, c_rsum2_obs, K, b0.rc, x0, y0, b0.vx, b0.vy, b0.radius, now, b0.ot, b0.oidx, b0.oarg);
         if (two) {
             const double x1 = bl_advance(b1.p0x, b1.vx, now, b1.t0), y1 = bl_advance(b1.p0y, b1.vy, now, b1.t0);
             T01 = bl_add(now, bl_toi_ball_ball<FMA>(x0, y0, b0.vx, b0.vy, x1, y1, b1.vx, b1.vy, rs01));
-            bl_next_obstacle<FMA>(s_obs, n_obs, P.rsum2_obs, K, b1.rc, x1, y1, b1.vx, b1.vy, b1.radius, now, b1.ot, b1.oidx, b1.oarg);
+            bl_next_obstacle<FMA>(s_obs, n_obs, c_rsum2_obs, K, b1.rc, x1, y1, b1.vx, b1.vy, b1.radius, now, b1.ot, b1.oidx, b1.oarg);
         }
     } else {
         b0.ot = P.obs_t[sb]; b0.oarg = P.obs_arg[sb]; b0.oidx = P.obs_idx[sb];

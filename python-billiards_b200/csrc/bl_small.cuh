@@ -34,6 +34,9 @@ struct SmallParams {
     uint64_t *cover_code;
     int64_t *seq_counter;
     // ensembles only
+    // per-system composition (bl_multi.per_system): radius / mass / rclass of system s start at [s * ball_stride],
+    // its (r_a + r_b)**2 tables at rsum2 + s * rs_stride and rsum2_obs + s * rso_stride; 0 = one set shared by all
+    long long ball_stride, rs_stride, rso_stride;
     int build_tables;          // solve every pair at the system's current time first (what add_ball does row by row)
     double *sys_time;
     int64_t *n_bb, *n_bo;

@@ -402,3 +402,66 @@ def test_library_calls_on_a_non_current_device(billiards, oracle):
     bb, bo = multi.evolve(100.0)
     assert (bb == 167).all() and (bo == 248).all()
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8, 16, 32, 40])
+def test_per_system_radii_and_masses_against_oracle(billiards, oracle, n):
+    """radius / mass of shape (S, n): every system of the ensemble has its own composition (per-system radius classes and
+    (r_a + r_b)**2 tables).  Each system == the oracle run on that system's balls, bit for bit; systems that share a
+    composition with the slot-wise ensemble give what it gives."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    rng = np.random.default_rng(700 + n)
+    S = 21 if n <= 32 else 6
+    obstacles, pos, vel, radius, mass = _small_gas(rng, n, S)
+    radii = np.repeat(radius[None], S, axis=0)
+    masses = np.repeat(mass[None], S, axis=0)
+    for s in range(1, S):  # system 0 keeps the shared composition
+        radii[s] = np.round(radius * rng.uniform(0.5, 1.1, n) * 1024.0) / 1024.0
+        masses[s] = mass * rng.uniform(0.3, 3.0, n)
+    if n >= 4:
+        radii[:, 3] = 0.0   # the point particle stays one (two of them never collide)
+    ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, radius=radii, mass=masses,
+                                     dot_fma=fma)
+    T = 9.0
+    c1 = ens.evolve(T / 3)
+    c2 = ens.evolve(T)
+    ens.run(15)
+    got_t, got_v, got_pos = ens.time, ens.balls_velocity, ens.balls_position
+    got_bb, got_bo, tables = ens.counts_ball_ball, ens.counts_ball_obstacle, ens.toi_tables
+    for s in range(S):
+        o = oracle.OracleBilliard(workloads.oracle_obstacles(obstacles), dot_fma=fma)
+        o.add_balls(pos[s], vel[s], radii[s], masses[s])
+        a, b = o.evolve(T / 3), o.evolve(T)
+        c = o.evolve(INF, max_events=15)
+        assert (int(c1[0][s]), int(c1[1][s])) == a and (int(c2[0][s]), int(c2[1][s])) == b, f"system {s}"
+        assert (int(got_bb[s]), int(got_bo[s])) == (a[0] + b[0] + c[0], a[1] + b[1] + c[1]), f"system {s}"
+        st = o.state()
+        assert got_t[s] == o.time, f"system {s}"
+        assert_bits_equal(got_v[s], st["v"], f"system {s}: velocities")
+        assert_bits_equal(got_pos[s], st["pos"], f"system {s}: positions")
+        rows = o.toi_table
+        for i in range(n):
+            assert_bits_equal(tables[s, i, :i], rows[i], f"system {s}: table row {i}")
+    shared = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos[:1], vel[:1], radius=radii[0],
+                                        mass=masses[0], dot_fma=fma)
+    shared.evolve(T / 3); shared.evolve(T); shared.run(15)
+    assert_bits_equal(shared.balls_velocity[0], got_v[0], "shared composition == per-system composition")
+
+
+def test_galperin_digits_of_pi_at_six_mass_ratios_in_one_launch(billiards):
+    """README.md:58-63, :114-135 of the reference (the number of collisions spells pi) as ONE ensemble: six two-ball
+    systems whose heavy ball weighs 100**k, k = 0 .. 5 -- per-system masses."""
+    from billiards import _lib
+    fma = _lib.probe_dot_fma()
+    cfg = workloads.galperin()
+    S = 6
+    pos = np.repeat(cfg.pos[None], S, axis=0)
+    vel = np.repeat(cfg.vel[None], S, axis=0)
+    mass = np.asarray([[1.0, 100.0 ** k] for k in range(S)])
+    ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, cfg.obstacles), pos, vel,
+                                     radius=np.repeat(cfg.radius[None], S, axis=0), mass=mass, dot_fma=fma)
+    bb, bo = ens.evolve(INF, max_collisions=10**6)
+    assert (bb + bo).tolist() == [3, 31, 314, 3141, 31415, 314159]
+    single = workloads.galperin().build(billiards, dot_fma=fma)
+    assert single.evolve(16) == (int(bb[5]), int(bo[5]))
