@@ -57,10 +57,23 @@ def main():
                 # the line again and again at one and the same time (it never returns from evolve; neither would the kernel)
                 radius = radius.copy()
                 radius[3] = radius[0]
+        per_system = rng.random() < 0.35   # every system its own radii and masses (bl_multi.per_system)
+        if per_system:
+            radii = np.repeat(np.asarray(radius)[None], S, axis=0)
+            masses = np.repeat(np.asarray(mass)[None], S, axis=0)
+            for s in range(1, S):
+                radii[s] = np.round(radii[s] * rng.uniform(0.5, 1.1, n) * 1024.0) / 1024.0
+                masses[s] = masses[s] * rng.uniform(0.3, 3.0, n)
+            if n >= 4 and len(obstacles) == 5 and obstacles[4][0] != "segment":
+                radii[:, 3] = 0.0
+            elif n >= 4:
+                radii[:, 3] = np.maximum(radii[:, 3], 1.0 / 64)  # (no point particle with a segment, see above)
+        else:
+            radii, masses = radius, mass
         T = float(rng.uniform(2.0, 9.0))
         cuts = sorted(rng.uniform(0.0, T, int(rng.integers(0, 3))).tolist()) + [T]
         extra = int(rng.integers(0, 40))
-        ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, radius=radius, mass=mass,
+        ens = billiards.BilliardEnsemble(workloads.make_obstacles(billiards, obstacles), pos, vel, radius=radii, mass=masses,
                                          dot_fma=fma)
         h.check(h.lib.bl_set_small_kernel(h.h, kernel))
         try:
@@ -75,7 +88,7 @@ def main():
         total = 0
         for s in range(S):
             o = oracle.OracleBilliard(workloads.oracle_obstacles(obstacles), dot_fma=fma)
-            o.add_balls(pos[s], vel[s], radius, mass)
+            o.add_balls(pos[s], vel[s], radii[s] if per_system else radius, masses[s] if per_system else mass)
             cb = co = 0
             for t in cuts:
                 a = o.evolve(t, max_events=200000)
@@ -94,7 +107,7 @@ def main():
                 print(f"MISMATCH multi case {case}: n={n} kernel={kernel} S={S} system {s} seed={seed}", flush=True)
                 sys.exit(1)
             total += cb + co
-        print(f"multi case {case}: n={n:2d} kernel={kernel} S={S:2d} obstacles={len(obstacles)} cuts={len(cuts)} extra={extra:2d} "
+        print(f"multi case {case}: n={n:2d} kernel={kernel} S={S:2d} obstacles={len(obstacles)} cuts={len(cuts)} extra={extra:2d} per_system={int(per_system)} "
               f"collisions={total} ok", flush=True)
         # a one-ball ensemble on a random geometry
         nw, nd = int(rng.integers(0, 5)), int(rng.integers(0, 2))
