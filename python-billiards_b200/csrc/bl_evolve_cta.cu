@@ -10,12 +10,14 @@
 //   -> every thread resolves the collision redundantly from the mirrored states
 //   -> every other thread re-solves its pair(s) with the colliding ball(s) and updates its cached row minimum; a thread
 //      whose minimum was a colliding ball, and the colliding balls themselves, are put on a list
-//   -> warp 0 solves the (ball, obstacle) pairs of the colliding balls spread over its lanes
+//   -> one warp solves the (ball, obstacle) pairs of the colliding balls spread over its lanes (ensembles: warp 0; a
+//      single system: an extra warp without balls, beside the pair solves of the others)
 //   -> the rows on the list are scanned again, one warp per row (the colliding balls' own cached minima simply start
 //      empty: all their pairs compete in the other balls' minima -- the "cover" of bl_evolve.cu).
-// Two __syncthreads per collision, a third when a row is listed (about every second collision).  Same arithmetic, keys, stop rules, log and result block as the lane-group
-// kernel (bl_evolve_small.cu), which it follows line by line where the two coincide; the same two front ends: a single
-// Billiard (SINGLE) and an ensemble of independent systems, one CTA each (bl_multi_run).
+// Two __syncthreads per collision, a third when a row is listed (about every second collision).  Same arithmetic,
+// keys, stop rules, log and result block as the lane-group kernel (bl_evolve_small.cu), which it follows line by line
+// where the two coincide; the same two front ends: a single Billiard (SINGLE) and an ensemble of independent systems,
+// one CTA each (bl_multi_run).
 //
 // Reference lines restated: simulation.py:354-438 (evolve), :440-502 (bounce_ball_ball), :504-554
 // (bounce_ball_obstacle), :556-560 (_move), :562-636 (resolve), :176-209 (add_ball's row, for table builds).
@@ -155,8 +157,10 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
     }
     int end_stop = BL_STOP_TIME, end_status = BL_OK;
     int par = 0, lp = 0;
-    long long pc[6] = {0, 0, 0, 0, 0, 0};  // phase clocks of thread 0
-    long long c0 = clock64();
+    // single systems: phase clocks (argmin, resolve, pair solves, obstacle solves, barrier, re-scan), reported by
+    // thread 0 in result.prof[8..13] (tools/cta_once.py); compiled out of the ensemble builds
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    long long c0 = SINGLE ? clock64() : 0;
 
     for (;;) {
         // ---- my key: the cached minimum of my table row (first index on ties), or my next obstacle ----
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             cd = take ? c2 : cd;
         }
         par ^= 1;
-        { const long long c1 = clock64(); pc[0] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[0] += c1 - c0; c0 = c1; }
 
         // ---- stop rules ----
         int stop_kind = -1, st_status = BL_OK;
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             break;
         }
 
-        { const long long c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[1] += c1 - c0; c0 = c1; }
         // ---- log, simulation.py:590-594 / :626-631 payloads ----
         if (want_log && li == 0) {
             const long long e = done;
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             ct = BL_INF; cj = -1; partial = true;
         }
         if (rescan) s_list[atomicAdd(&s_misc[lp], 1)] = li;
-        { const long long c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[2] += c1 - c0; c0 = c1; }
         // ---- next obstacle of the colliding balls (:490-495, :545-547), spread over the lanes of warp 0: lane l takes
         // the obstacles (l >> 1), (l >> 1) + 16, ... for ball a (even lanes) or b (odd lanes); the partial minima are
         // combined by a butterfly over the lanes of equal parity -- smaller time, then smaller list index, which is the
@@ -366,9 +370,9 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             }
             if (lane < 2) { s_obr[2 * lane] = omin; s_obr[2 * lane + 1] = oam; s_misc[2 + lane] = oq; }
         }
-        { const long long c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[3] += c1 - c0; c0 = c1; }
         __syncthreads();  // table entries, mirrored states, the list and the obstacle results are in place
-        { const long long c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[4] += c1 - c0; c0 = c1; }
         // ---- the listed rows again, one warp per row ----
         int nl;
         {
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(32 * (MAXW + (SINGLE ? 1 : 0)), (SINGLE || MAX
             __syncthreads();  // re-scanned minima in place
             if (rescan) { ct = s_ct[li]; cj = s_cj[li]; }
         }
-        { const long long c1 = clock64(); pc[5] += c1 - c0; c0 = c1; }
+        if (SINGLE) { const long long c1 = clock64(); pc[5] += c1 - c0; c0 = c1; }
         done++;
         n_bb += b >= 0 ? 1 : 0;
         now = t;
